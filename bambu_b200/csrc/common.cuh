@@ -1,0 +1,130 @@
+// common.cuh -- shared definitions of the device code (sm_100a only).
+//
+// Vocabulary: a *gene group* is the unit of one emWithL1 call in the reference
+// (R/bambu-quantify_utilityFunctions.R:401-431); its *image* is the compacted,
+// doubly-ordered copy of its compatibility slice that the EM kernels iterate on.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bambu {
+
+// ---- raw arena, device pointers (include/bambu_em.h) -------------------------
+struct ArenaDev {
+    const int64_t *grp_row_ptr, *grp_col_ptr, *row_nnz_ptr;
+    const int32_t *col_idx;
+    const double *aval;
+    const uint8_t *nz_flags;
+    const double *Y, *K;
+    const uint8_t *col_flags;
+    int64_t n_groups, total_rows;
+};
+
+// ---- what the pack kernel found in a group ------------------------------------
+struct PackInfo {
+    int32_t NL;     // live columns: Y != 0
+    int32_t nnzL;   // entries with aval != 0 in live columns
+};
+
+// ---- image of a resident-tier group -------------------------------------------
+// A group's EM only ever needs the columns with Y_j != 0 ("live"): a column with
+// Y_j == 0 has ratio Y_j/c_j in {0, NaN}, so every term it adds to a row sum is
+// +-0 or NaN->0 (src/em.cpp:48-49), and its baseSum K_j*Y_j/c_j is 0 or NaN->0
+// (src/em.cpp:98-99); c_j itself is used nowhere else.  Entries with aval == 0
+// are no-ops for the same reason.  rs_i (src/em.cpp:33) still sums ALL entries.
+// The position parity that selects Armadillo's accumulator (even index ->
+// acc1, odd -> acc2) is kept in bit 0 of every index.
+//
+//   [rs f64 M][Yl f64 NL][cval f64 nnzL][rval f64 nnzL]
+//   [rp u16 M+1][cp u16 NL+1][cidx u16 nnzL][ridx u16 nnzL]      <- copied to shared memory
+//   [KY f64 NL][eq u8 nnzL][cm u8 NL]                            <- read once, in the epilogue
+//
+//   cval/cidx: row-major (row i = [rp[i], rp[i+1])), cidx = live_col<<1 | (orig_col&1)
+//   rval/ridx: column-major (col j = [cp[j], cp[j+1])), ridx = row<<1 | (row&1), rows ascending
+struct ImgLayout {
+    uint32_t rs, Yl, cval, rval, rp, cp, cidx, ridx, copy_bytes, KY, eq, cm, total;
+};
+
+__host__ __device__ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
+
+__host__ __device__ inline ImgLayout img_layout(uint32_t M, uint32_t NL, uint32_t nnzL)
+{
+    ImgLayout L;
+    L.rs = 0;
+    L.Yl = L.rs + 8u * M;
+    L.cval = L.Yl + 8u * NL;
+    L.rval = L.cval + 8u * nnzL;
+    L.rp = L.rval + 8u * nnzL;
+    L.cp = L.rp + 2u * (M + 1);
+    L.cidx = L.cp + 2u * (NL + 1);
+    L.ridx = L.cidx + 2u * nnzL;
+    L.copy_bytes = align_up(L.ridx + 2u * nnzL, 16);
+    L.KY = L.copy_bytes;
+    L.eq = L.KY + 8u * NL;
+    L.cm = L.eq + nnzL;
+    L.total = align_up(L.cm + NL, 16);
+    return L;
+}
+
+// shared-memory bytes the resident EM kernel needs for a group (image + theta + ratio)
+__host__ __device__ inline uint32_t em_smem_bytes(uint32_t M, uint32_t NL, uint32_t nnzL)
+{
+    return img_layout(M, NL, nnzL).copy_bytes + 8u * M + 8u * NL;
+}
+
+// shared-memory bytes the pack kernel needs for a group
+__host__ __device__ inline uint32_t pack_smem_bytes(uint32_t M, uint32_t N)
+{
+    return 4u * (N + (M + 1) + (N + 1) + N);
+}
+
+constexpr uint32_t kSmemMax = 227u * 1024u - 256u;  // per-CTA opt-in maximum minus static shared
+constexpr int kMaxIndex = 32767;                    // u16 index carries a parity bit
+
+// error codes written to the device error word by the kernels
+constexpr int kErrColRange = 1;   // col_idx outside [0, N)
+constexpr int kErrColOrder = 2;   // col_idx not strictly increasing inside a row
+
+// ---- block-wide exclusive scan, in place, n arbitrary ---------------------------
+template <int T>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t *a, int n, uint32_t *s_warp /* 34 words */)
+{
+    const int tid = threadIdx.x;
+    const int chunk = (n + T - 1) / T;
+    const int lo = min(n, tid * chunk), hi = min(n, lo + chunk);
+    uint32_t sum = 0;
+    for (int k = lo; k < hi; ++k) sum += a[k];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((tid & 31) >= o) incl += v;
+    }
+    if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+        uint32_t w = (tid < T / 32) ? s_warp[tid] : 0u;
+        uint32_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (tid >= o) wi += v;
+        }
+        s_warp[tid] = wi - w;
+        if (tid == 31) s_warp[32] = wi;
+    }
+    __syncthreads();
+    uint32_t run = s_warp[tid >> 5] + (incl - sum);
+    const uint32_t total = s_warp[32];
+    for (int k = lo; k < hi; ++k) {
+        uint32_t t = a[k];
+        a[k] = run;
+        run += t;
+    }
+    __syncthreads();
+    return total;
+}
+
+__device__ __forceinline__ bool is_finite(double x) { return fabs(x) <= 1.7976931348623157e308; }
+
+}  // namespace bambu

@@ -1,0 +1,326 @@
+"""Host-side mirror of the reference's quantification stage around the EM.
+
+Same names and argument meaning as the reference (bambu 3.3.5):
+
+    bambu_quantDT(readClassDt, emParameters)      R/bambu-quantify.R:53-74
+      addAval                                      R/bambu-quantify_utilityFunctions.R:196-230
+        simplifyNames / calculateDegradationRate / modifyAvaluewithDegradation_rate /
+        removeUnObservedGenes                      :236-315
+      initialiseOutput / filterTxRc / assignGroups :322-356
+      pack_arena  (getInputList + getAMat, as one segmented-CSR arena instead of
+                   per-group lists and dense matrices)   :359-371, 401-431
+      abundance_quantification  -> ONE call into libbambu_em.so (bambu_b200.em)
+      modifyQuantOut / removeDuplicates            :438-455
+    calculateCPM                                   :493-497
+    setEmParameters                                R/bambu_utilityFunctions.R:48-53
+
+``readClassDt`` is the long table as a dict of equal-length arrays with the
+columns ``GENEID, txid, eqClassId, nobs, equal, rcWidth, txlen``
+(R/bambu-quantify_utilityFunctions.R:199-203).  Everything is vectorised numpy;
+R's ``sum()`` accumulates in long double, restated with ``numpy.longdouble``
+added in table order.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .arena import Arena
+
+LD = np.longdouble
+
+
+def setEmParameters(emParameters=None):
+    """R/bambu_utilityFunctions.R:48-53 (defaults as coded, not as documented)."""
+    defaults = {"degradationBias": True, "maxiter": 10000, "conv": 1e-2, "minvalue": 1e-8, "sig.digit": 5}
+    if emParameters:
+        for k, v in emParameters.items():
+            defaults[k] = v   # unknown keys are kept, like updateParameters (:59-68)
+    return defaults
+
+
+# ------------------------------------------------------------------ helpers
+def _first_appearance_rank(*keys):
+    """Dense 0-based id of each row's key tuple, numbered by first appearance
+    (R: match(x, unique(x)))."""
+    n = len(keys[0])
+    if n == 0:
+        return np.zeros(0, np.int64), 0
+    order = np.lexsort(tuple(reversed(keys)))
+    sk = [k[order] for k in keys]
+    new = np.ones(n, bool)
+    new[1:] = np.any([s[1:] != s[:-1] for s in sk], axis=0)
+    sorted_id = np.cumsum(new) - 1
+    ident = np.empty(n, np.int64)
+    ident[order] = sorted_id
+    first_pos = np.full(int(sorted_id[-1]) + 1, n, np.int64)
+    np.minimum.at(first_pos, ident, np.arange(n))
+    rank_of_id = np.empty(len(first_pos), np.int64)
+    rank_of_id[np.argsort(first_pos, kind="stable")] = np.arange(len(first_pos))
+    return rank_of_id[ident], len(first_pos)
+
+
+def _r_sum_by(idx, vals, n):
+    """R ``sum()`` per group: long double accumulator, rows added in table order."""
+    acc = np.zeros(n, dtype=LD)
+    np.add.at(acc, idx, vals.astype(LD))
+    return acc.astype(np.float64)
+
+
+def _r_median(x):
+    x = np.sort(x[~np.isnan(x)])
+    n = len(x)
+    if n == 0:
+        return float("nan")
+    if n % 2:
+        return float(x[n // 2])
+    a, b = LD(x[n // 2 - 1]), LD(x[n // 2])
+    s = (a + b) / LD(2)                       # R mean(): long double sum / n ...
+    t = ((a - s) + (b - s)) / LD(2)           # ... plus one refinement pass
+    return float(s + t)
+
+
+# ------------------------------------------------------------------ addAval
+def calculateDegradationRate(gene_sid, eqClassId, nobs, equal, txlen, n_genes):
+    """R/bambu-quantify_utilityFunctions.R:247-269.  Returns (d_rate, n_genes_used)."""
+    cls_id, n_cls = _first_appearance_rank(gene_sid, eqClassId, nobs)
+    first = np.zeros(n_cls, np.int64)
+    first[cls_id[::-1]] = np.arange(len(cls_id))[::-1]
+    g_of = gene_sid[first]
+    gene_nobs = _r_sum_by(g_of, nobs[first], n_genes)
+    has = np.zeros(n_genes, bool)
+    has[g_of] = True
+    par = ~equal
+    pid, n_p = _first_appearance_rank(gene_sid[par], eqClassId[par], nobs[par])
+    pfirst = np.zeros(n_p, np.int64)
+    pfirst[pid[::-1]] = np.arange(len(pid))[::-1]
+    pg = gene_sid[par][pfirst]
+    dobs = _r_sum_by(pg, nobs[par][pfirst], n_genes)
+    has_par = np.zeros(n_genes, bool)
+    has_par[pg] = True
+    dobs = np.where(has_par, dobs, np.nan)
+    gene_len = np.full(n_genes, -np.inf)
+    np.maximum.at(gene_len, gene_sid, txlen)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        rate = dobs / gene_nobs
+        keep = has & (gene_nobs >= 30) & ((gene_nobs - dobs) >= 5)      # NA comparisons are not TRUE
+        sel = keep if keep.any() else has
+        vals = rate[sel] * 1000 / gene_len[sel]
+    return _r_median(vals), int(sel.sum())
+
+
+def modifyAvaluewithDegradation_rate(gene_sid, txid, eqClassId, equal, rcWidth, d_rate, d_mode):
+    """R/bambu-quantify_utilityFunctions.R:276-296.  Returns (aval, multi_align)."""
+    n = len(txid)
+    cls, n_cls = _first_appearance_rank(eqClassId, gene_sid)
+    trip, n_trip = _first_appearance_rank(eqClassId, gene_sid, txid)
+    tfirst = np.zeros(n_trip, np.int64)
+    tfirst[trip[::-1]] = np.arange(n)[::-1]
+    ntx = np.bincount(cls[tfirst], minlength=n_cls)
+    multi = ntx[cls] > 1
+    if not d_mode:
+        return np.ones(n), multi
+    aval = np.full(n, np.nan)
+    part = rcWidth * d_rate / 1000
+    gt, n_gt = _first_appearance_rank(gene_sid, txid)
+    m = multi
+    psum = _r_sum_by(gt[m & ~equal], part[m & ~equal], n_gt)
+    aval[m] = np.where(equal[m], 1 - psum[gt[m]], part[m])
+    if d_rate == 0:
+        allpar = np.ones(n_cls, bool)
+        np.logical_and.at(allpar, cls, (~equal) & multi)
+        aval[allpar[cls]] = 0.01
+    with np.errstate(invalid="ignore"):
+        aval = np.where(np.isnan(aval), aval, np.maximum(np.minimum(aval, 1.0), 0.0))
+        me = multi & equal
+        aval[me] = np.minimum(1.0, np.maximum(aval[me], part[me]))
+    aval[~multi] = 1.0
+    return aval, multi
+
+
+# ------------------------------------------------------------------ packing
+class PackedQuant:
+    """Everything ``bambu_quantDT`` needs after the EM: the arena plus the
+    bookkeeping of ``initialiseOutput`` / ``removeUnObservedGenes``."""
+
+    def __init__(self):
+        self.arena: Arena | None = None
+        self.d_rate = float("nan")
+        self.out_txid = np.zeros(0, np.int64)          # initialiseOutput row order
+        self.unobserved_txid = np.zeros(0, np.int64)   # removeUnObservedGenes rows
+        self.gene_grp_id = np.zeros(0, np.int64)       # per arena group
+
+
+def pack_quantDT(readClassDt, emParameters=None) -> PackedQuant:
+    """Everything of ``bambu.quantDT`` up to (not including) the EM
+    (R/bambu-quantify.R:53-62): the long table -> one arena."""
+    par = setEmParameters(emParameters)
+    need = ("GENEID", "txid", "eqClassId", "nobs")
+    if readClassDt is None:
+        raise ValueError("Input object is missing.")
+    if any(k not in readClassDt for k in need):
+        raise ValueError("Columns GENEID, txid, eqClassId, nobs, are missing from object.")
+    n = len(readClassDt["txid"])
+    txid = np.asarray(readClassDt["txid"]).astype(np.int64)
+    eqc = np.asarray(readClassDt["eqClassId"]).astype(np.int64)
+    nobs = np.asarray(readClassDt["nobs"], dtype=np.float64)
+    equal = np.asarray(readClassDt["equal"], dtype=bool) if "equal" in readClassDt else np.zeros(n, bool)
+    rcw = np.asarray(readClassDt.get("rcWidth", np.zeros(n)), dtype=np.float64)
+    txlen = np.asarray(readClassDt.get("txlen", np.ones(n)), dtype=np.float64)
+    gid = np.asarray(readClassDt["GENEID"])
+    out = PackedQuant()
+
+    gene_sid, n_genes = _first_appearance_rank(gid)              # simplifyNames (0-based here)
+    d_mode = bool(par["degradationBias"])
+    if d_mode:
+        out.d_rate, _ = calculateDegradationRate(gene_sid, eqc, nobs, equal, txlen, n_genes)
+    aval, multi = modifyAvaluewithDegradation_rate(gene_sid, txid, eqc, equal, rcw, out.d_rate, d_mode)
+
+    # removeUnObservedGenes (:301-315)
+    gsum = _r_sum_by(gene_sid, nobs, n_genes)
+    uo = gsum[gene_sid] == 0
+    if uo.any():
+        pid, npair = _first_appearance_rank(txid[uo], gene_sid[uo])
+        first = np.zeros(npair, np.int64)
+        first[pid[::-1]] = np.arange(int(uo.sum()))[::-1]
+        out.unobserved_txid = txid[uo][first]
+    keep = ~uo
+    gene_sid, txid, eqc, nobs, equal, aval, multi = (x[keep] for x in (gene_sid, txid, eqc, nobs, equal, aval, multi))
+
+    # K, n.obs (:221-228); the right_join orders rows by first appearance of (gene_sid, eqClassId)
+    cls3, n3 = _first_appearance_rank(gene_sid, eqc, nobs)
+    f3 = np.zeros(n3, np.int64)
+    f3[cls3[::-1]] = np.arange(len(cls3))[::-1]
+    Kg = _r_sum_by(gene_sid[f3], nobs[f3], n_genes)
+    cls2, _ = _first_appearance_rank(gene_sid, eqc)
+    order = np.argsort(cls2, kind="stable")
+    gene_sid, txid, eqc, nobs, equal, aval, multi = (x[order] for x in (gene_sid, txid, eqc, nobs, equal, aval, multi))
+    K = Kg[gene_sid]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        n_obs = nobs / K
+
+    # initialiseOutput (:322-327)
+    tid, ntx = _first_appearance_rank(txid)
+    tfirst = np.zeros(ntx, np.int64)
+    tfirst[tid[::-1]] = np.arange(len(tid))[::-1]
+    out.out_txid = txid[tfirst]
+
+    # filterTxRc (:332-342)
+    gt, n_gt = _first_appearance_rank(gene_sid, txid)
+    tsum = _r_sum_by(gt, nobs, n_gt)
+    kp = tsum[gt] > 0
+    gene_sid, txid, eqc, equal, aval, multi, K, n_obs = (x[kp] for x in (gene_sid, txid, eqc, equal, aval, multi, K, n_obs))
+    order = np.lexsort((eqc, txid, gene_sid))
+    gene_sid, txid, eqc, equal, aval, multi, K, n_obs = (x[order] for x in (gene_sid, txid, eqc, equal, aval, multi, K, n_obs))
+
+    # assignGroups (:347-356)
+    gtx, _ = _first_appearance_rank(gene_sid, txid)
+    geq, _ = _first_appearance_rank(gene_sid, eqc)
+    genes = np.unique(gene_sid)                                   # ascending = table order
+    gpos = np.searchsorted(genes, gene_sid)
+
+    def n_distinct(ids):
+        u = np.unique(np.stack((gpos, ids), axis=1), axis=0) if len(ids) else np.zeros((0, 2), np.int64)
+        return np.bincount(u[:, 0], minlength=len(genes))
+    tr_dim = n_distinct(gtx) * n_distinct(geq)
+    sorder = np.argsort(tr_dim, kind="stable")
+    grp_of_gene = np.empty(len(genes), np.int64)
+    grp_of_gene[sorder] = np.cumsum(tr_dim[sorder]) // 1000 + 1
+    grp = grp_of_gene[gpos]
+
+    # getInputList + getAMat (:359-371, 427-431) as one arena
+    gids = np.unique(grp)
+    gi = np.searchsorted(gids, grp)
+    G = len(gids)
+    # rows: unique (group, txid) sorted; columns: unique (group, gene_sid, eqClassId) sorted
+    rkey = np.unique(np.stack((gi, txid), axis=1), axis=0) if n else np.zeros((0, 2), np.int64)
+    ckey = np.unique(np.stack((gi, gene_sid, eqc), axis=1), axis=0) if n else np.zeros((0, 3), np.int64)
+    grp_row_ptr = np.concatenate(([0], np.cumsum(np.bincount(rkey[:, 0], minlength=G)))).astype(np.int64)
+    grp_col_ptr = np.concatenate(([0], np.cumsum(np.bincount(ckey[:, 0], minlength=G)))).astype(np.int64)
+
+    def locate(keys, *cols):
+        """index of each table row's key among the sorted unique keys"""
+        # encode lexicographically via searchsorted on a structured view
+        kv = np.ascontiguousarray(keys).view([("", keys.dtype)] * keys.shape[1]).ravel()
+        q = np.ascontiguousarray(np.stack(cols, axis=1)).view([("", keys.dtype)] * keys.shape[1]).ravel()
+        return np.searchsorted(kv, q)
+    if len(txid):
+        rrow = locate(rkey, gi, txid)
+        rcol = locate(ckey, gi, gene_sid, eqc)
+    else:
+        rrow = rcol = np.zeros(0, np.int64)
+    # Y / K / multi per column must be unique (the reference takes unique(...) there)
+    Ycol = np.full(len(ckey), np.nan)
+    Kcol = np.full(len(ckey), np.nan)
+    Ycol[rcol] = n_obs
+    Kcol[rcol] = K
+    if np.any((Ycol[rcol] != n_obs) & ~(np.isnan(Ycol[rcol]) & np.isnan(n_obs))):
+        raise ValueError("an equivalence class carries more than one nobs value")
+    mcol = np.zeros(len(ckey), np.uint8)
+    mcol[rcol] = multi.astype(np.uint8)
+    eorder = np.lexsort((rcol, rrow))
+    rrow_s, rcol_s = rrow[eorder], rcol[eorder]
+    if len(rrow_s) > 1 and np.any((rrow_s[1:] == rrow_s[:-1]) & (rcol_s[1:] == rcol_s[:-1])):
+        raise ValueError("duplicated (txid, gene, eqClassId) rows in readClassDt")
+    row_nnz_ptr = np.concatenate(([0], np.cumsum(np.bincount(rrow_s, minlength=len(rkey))))).astype(np.int64)
+    grp_of_row = rkey[:, 0]
+    col_idx = (rcol_s - grp_col_ptr[grp_of_row[rrow_s]]).astype(np.int32)
+    out.arena = Arena(grp_row_ptr, grp_col_ptr, row_nnz_ptr, col_idx, aval[eorder].astype(np.float64),
+                      equal[eorder].astype(np.uint8), Ycol, Kcol, mcol, rkey[:, 1].astype(np.int32))
+    out.gene_grp_id = gids
+    return out
+
+
+# ------------------------------------------------------------------ the stage
+def bambu_quantDT(readClassDt, emParameters=None, verbose=False, em=None, details=None):
+    """``bambu.quantDT`` (R/bambu-quantify.R:53-74).
+
+    Returns a dict ``txid, counts, fullLengthCounts, uniqueCounts`` (arrays) in
+    the row order of the reference's result table.  ``em`` is the callable that
+    stands in for ``abundance_quantification`` -- by default the CUDA library
+    (``bambu_b200.em.abundance_quantification``); tests may pass the CPU oracle."""
+    par = setEmParameters(emParameters)
+    pk = pack_quantDT(readClassDt, par)
+    if em is None:
+        from .em import abundance_quantification as em
+    a = pk.arena
+    if a.n_groups:
+        est, iters, status = em(a, maxiter=par["maxiter"], conv=par["conv"], minvalue=par["minvalue"])
+    else:
+        est, iters, status = np.zeros((3, 0)), np.zeros(0, np.int32), np.zeros(0, np.int32)
+    if details is not None:
+        details.update({"d_rate": pk.d_rate, "arena": a, "iters": iters, "status": status, "est": est,
+                        "gene_grp_id": pk.gene_grp_id})
+    return modifyQuantOut_removeDuplicates(pk, est)
+
+
+def modifyQuantOut_removeDuplicates(pk: PackedQuant, est):
+    """``modifyQuantOut`` (positional; a txid estimated in several groups keeps
+    the last group's value), ``rbind`` of the unobserved genes' zero rows, then
+    ``removeDuplicates`` (sum by txid, first-appearance order)
+    (R/bambu-quantify_utilityFunctions.R:438-455, R/bambu-quantify.R:70-72)."""
+    a = pk.arena
+    out_txid = pk.out_txid
+    vals = np.zeros((3, len(out_txid)))
+    if a.n_rows:
+        srt = np.argsort(out_txid, kind="stable")
+        pos = srt[np.searchsorted(out_txid[srt], a.txid)]
+        vals[:, pos] = est            # later rows overwrite earlier ones: last group wins
+    all_tx = np.concatenate((pk.unobserved_txid, out_txid))
+    all_vals = np.concatenate((np.zeros((3, len(pk.unobserved_txid))), vals), axis=1)
+    tid, ntx = _first_appearance_rank(all_tx)
+    first = np.zeros(ntx, np.int64)
+    first[tid[::-1]] = np.arange(len(tid))[::-1]
+    res = {"txid": all_tx[first]}
+    for k, name in enumerate(("counts", "fullLengthCounts", "uniqueCounts")):
+        res[name] = _r_sum_by(tid, all_vals[k], ntx)
+    return res
+
+
+def calculateCPM(counts, incompatibleCounts=0.0):
+    """R/bambu-quantify_utilityFunctions.R:493-497:
+    ``counts / (sum(counts) + sum(incompatible counts)) * 1e6`` (R long double sums)."""
+    counts = np.asarray(counts, dtype=np.float64)
+    inc = np.atleast_1d(np.asarray(incompatibleCounts, dtype=np.float64))
+    seq = lambda v: (np.cumsum(v.astype(LD))[-1] if len(v) else LD(0))   # sequential, like R  # noqa: E731
+    tot = float(seq(counts) + seq(inc))
+    return counts / tot * 1e6

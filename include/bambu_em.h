@@ -1,0 +1,152 @@
+/*
+ * bambu_em.h -- C ABI of the B200-native quantification EM (libbambu_em.so).
+ *
+ * This library replaces, for one whole sample (or many samples) at a time,
+ * what the reference bambu 3.3.5 does per gene group through
+ *
+ *     abundance_quantification()  R/bambu-quantify_utilityFunctions.R:379-391
+ *       run_parallel()            R/bambu-quantify_utilityFunctions.R:401-425
+ *         getAMat() x3            R/bambu-quantify_utilityFunctions.R:427-431
+ *         emWithL1()              R/RcppExports.R:12-14 -> src/RcppExports.cpp:31-46
+ *           em_theta()            src/em.cpp:9-71
+ *           3 weighted row sums   src/em.cpp:97-102
+ *
+ * i.e. one call here == the reference's serial lapply over all gene groups,
+ * each of which is one .Call("_bambu_emWithL1", A, A_full, A_unique, Y, K,
+ * maxiter, minvalue, conv) (R/RcppExports.R:13).
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; caller owns every buffer passed in; the
+ *     library never keeps a caller pointer after the call returns (except the
+ *     *_bind_device call, which says so);
+ *   - every function returns BAMBU_EM_OK (0) or a negative error code and
+ *     never throws or longjmps (the reference turns C++ exceptions into R
+ *     errors with BEGIN_RCPP/END_RCPP, src/RcppExports.cpp:32,45; an R shim
+ *     turns a non-zero code into stop(bambu_em_last_error()));
+ *   - there is NO CPU fallback: without a usable sm_100 device the calls fail
+ *     with BAMBU_EM_ENODEVICE;
+ *   - one host thread per process may drive a plan at a time (R is single
+ *     threaded; BiocParallel workers are processes, R/bambu_utilityFunctions.R:6-15).
+ *
+ * Arena (segmented CSR; see bambu_b200/arena.py for the prose version)
+ *   group g owns rows    [grp_row_ptr[g], grp_row_ptr[g+1])   (transcripts, txid ascending)
+ *           and columns  [grp_col_ptr[g], grp_col_ptr[g+1])   (read classes, (gene_sid, eqClassId) ascending)
+ *   row r   owns entries [row_nnz_ptr[r], row_nnz_ptr[r+1])   col_idx local to the group,
+ *                                                             strictly increasing inside a row
+ *   aval      = the "aval" column of the long table              (A      of src/em.cpp:77)
+ *   nz_flags  bit0 = equal        => A_full   = aval * equal     (R/...utilityFunctions.R:337)
+ *   col_flags bit0 = multi_align  => A_unique = aval * !multi    (R/...utilityFunctions.R:336)
+ *   Y = n.obs per column, K = K per column                       (R/...utilityFunctions.R:359-371)
+ *
+ * Outputs
+ *   est[3 * total_rows]  est[k*total_rows + r]: k = 0 counts, 1 fullLengthCounts,
+ *                        2 uniqueCounts  (rows of emWithL1's "theta", src/em.cpp:104-107)
+ *   iters[n_groups]      EM updates done for the group (the `iter` em_theta computes at
+ *                        src/em.cpp:45,69 and emWithL1 drops at :93-94); 0 for
+ *                        single-transcript groups (closed form, R/...utilityFunctions.R:410-414)
+ *   status[n_groups]     bit0: stopped by maxiter, bit1: non-finite estimate in the group
+ */
+#ifndef BAMBU_EM_H
+#define BAMBU_EM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BAMBU_EM_OK            0
+#define BAMBU_EM_EINVAL      (-1)  /* malformed arena / arguments                    */
+#define BAMBU_EM_ENODEVICE   (-2)  /* no usable sm_100 CUDA device                   */
+#define BAMBU_EM_ECUDA       (-3)  /* CUDA runtime error (see bambu_em_last_error)   */
+#define BAMBU_EM_ENOMEM      (-4)  /* host or device allocation failed               */
+#define BAMBU_EM_ESTATE      (-5)  /* plan used out of order                         */
+
+#define BAMBU_EM_STATUS_MAXITER    1
+#define BAMBU_EM_STATUS_NONFINITE  2
+
+#define BAMBU_NZ_EQUAL   1
+#define BAMBU_COL_MULTI  1
+
+/* ---- library-level ---------------------------------------------------------- */
+const char *bambu_em_version(void);
+/* message of the last failing call on this thread ("" if none) */
+const char *bambu_em_last_error(void);
+/* number of usable devices (sm_100); <0 on error */
+int bambu_em_device_count(void);
+/* select the device used by subsequent calls of this process (default 0) */
+int bambu_em_set_device(int device);
+/* free the cached workspace of bambu_em_batched (optional; R: .onUnload,
+ * R/bambu-quantify_utilityFunctions.R:505-507) */
+int bambu_em_shutdown(void);
+
+/* ---- one-shot, host buffers: the drop-in for abundance_quantification ----------
+ * Replaces R/bambu-quantify.R:64-66.  All pointers are HOST pointers.  Copies the
+ * arena to the device (pipelined in chunks of groups), runs the kernels, copies
+ * est/iters/status back, returns when the outputs are complete. */
+int bambu_em_batched(int64_t n_groups,
+                     const int64_t *grp_row_ptr, const int64_t *grp_col_ptr,
+                     const int64_t *row_nnz_ptr, const int32_t *col_idx, const double *aval,
+                     const uint8_t *nz_flags, const double *Y, const double *K,
+                     const uint8_t *col_flags,
+                     int32_t maxiter, double minvalue, double conv,
+                     double *est, int32_t *iters, int32_t *status);
+
+/* ---- one dense group: the drop-in for one emWithL1 call ------------------------
+ * Replaces .Call("_bambu_emWithL1", ...) (R/RcppExports.R:13, src/em.cpp:77-110).
+ * A, A_full, A_unique: M x N column-major (R matrices); Y, K: N.  est: 3 x M
+ * column-major, i.e. est[3*i + k] -- the layout of the "theta" matrix emWithL1
+ * returns.  iters_out may be NULL. */
+int bambu_emWithL1(const double *A, const double *A_full, const double *A_unique,
+                   const double *Y, const double *K, int32_t M, int32_t N,
+                   int32_t maxiter, double minvalue, double conv,
+                   double *est, int32_t *iters_out);
+
+/* ---- plan API: arena resident in HBM, repeated runs, caller-visible stream ------- */
+typedef struct bambu_em_plan bambu_em_plan;
+
+/* Analyse the group structure (HOST pointer arrays), build the size buckets and
+ * work queues, allocate device memory for the arena, the packed group images
+ * and the outputs. */
+int bambu_em_plan_create(bambu_em_plan **plan, int64_t n_groups,
+                         const int64_t *grp_row_ptr, const int64_t *grp_col_ptr,
+                         const int64_t *row_nnz_ptr);
+int bambu_em_plan_destroy(bambu_em_plan *plan);
+/* stream all work of this plan is ordered on (a cudaStream_t passed as void*);
+ * NULL = the plan's own stream.  Lets a harness bracket runs with its own events. */
+int bambu_em_plan_set_stream(bambu_em_plan *plan, void *cuda_stream);
+/* asynchronous H2D of the arena payload from HOST buffers (pinned => truly async) */
+int bambu_em_plan_upload(bambu_em_plan *plan, const int32_t *col_idx, const double *aval,
+                         const uint8_t *nz_flags, const double *Y, const double *K,
+                         const uint8_t *col_flags);
+/* use DEVICE buffers owned by the caller as the arena payload (no copy; the
+ * pointers must stay valid until the plan is destroyed or re-bound) */
+int bambu_em_plan_bind_device(bambu_em_plan *plan, const int32_t *d_col_idx, const double *d_aval,
+                              const uint8_t *d_nz_flags, const double *d_Y, const double *d_K,
+                              const uint8_t *d_col_flags);
+/* enqueue pack + EM kernels (asynchronous) */
+int bambu_em_plan_run(bambu_em_plan *plan, int32_t maxiter, double minvalue, double conv);
+/* asynchronous D2H of the outputs into HOST buffers, then wait for completion.
+ * Any of the pointers may be NULL.  nnz_nonzero[n_groups] receives, per group,
+ * the number of entries with aval != 0 (the nnz_g of the nnz-iterations metric). */
+int bambu_em_plan_download(bambu_em_plan *plan, double *est, int32_t *iters, int32_t *status,
+                           int64_t *nnz_nonzero);
+/* what the pack kernels kept per group: live columns (Y != 0) and the entries with
+ * aval != 0 inside them -- the part of the group the EM loop actually iterates on */
+int bambu_em_plan_download_live(bambu_em_plan *plan, int32_t *live_cols, int32_t *live_nnz);
+int bambu_em_plan_sync(bambu_em_plan *plan);
+/* device pointers of the outputs (est: 3*total_rows f64; iters, status: n_groups i32) */
+int bambu_em_plan_device_outputs(bambu_em_plan *plan, double **d_est, int32_t **d_iters,
+                                 int32_t **d_status);
+/* device time of the last completed run, from CUDA events on the launch stream:
+ * pack kernels, EM kernels, whole run.  Waits for the run. */
+int bambu_em_plan_last_run_ms(bambu_em_plan *plan, float *pack_ms, float *em_ms, float *total_ms);
+/* kernels launched by the last run */
+int bambu_em_plan_last_run_launches(bambu_em_plan *plan, int32_t *n_launches);
+/* bytes of device memory held by the plan */
+int bambu_em_plan_device_bytes(bambu_em_plan *plan, int64_t *bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAMBU_EM_H */

@@ -1,0 +1,206 @@
+"""Parity of the CUDA path (through the C-ABI) with the CPU oracle.
+
+Bar (BASELINE.json north_star): indexing and iteration counts exact; counts
+within 1e-6 relative / 1e-9 absolute.  The resident tier reproduces the
+reference's summation order, so these tests ask for more: identical doubles."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import assert_same_doubles, random_arena
+
+pytestmark = pytest.mark.gpu
+
+REL, ABS = 1e-6, 1e-9     # the tolerance north_star states
+
+
+@pytest.fixture(scope="module")
+def em():
+    from bambu_b200 import _lib
+    import bambu_b200.em as em_mod
+    L = _lib.lib()
+    assert L.bambu_em_device_count() >= 1, "no sm_100 device: the CUDA path cannot be exercised"
+    return em_mod
+
+
+def check_against_oracle(em, oracle_mod, arena, exact=True, **par):
+    est, iters, status = em.abundance_quantification(arena, **{"maxiter": 10000, **par})
+    o_est, o_it, o_st = oracle_mod.em_batched(arena, mode=oracle_mod.MODE_SPARSE, **{"maxiter": 10000, **par})
+    assert np.array_equal(iters, o_it), f"iteration counts differ in {np.count_nonzero(iters != o_it)} groups"
+    assert np.array_equal(status, o_st)
+    if exact:
+        assert_same_doubles(est, o_est, "est")
+    else:
+        assert np.array_equal(np.isnan(est), np.isnan(o_est))
+        ok = np.isclose(est, o_est, rtol=REL, atol=ABS, equal_nan=True)
+        assert ok.all()
+    return est, iters, status
+
+
+@pytest.mark.parametrize("bias,key", [(False, "estOutput_woBC"), (True, "estOutput_wBC")])
+def test_reference_goldens_through_cuda(em, unit_goldens, bias, key):
+    """tests/testthat/test_quant.R:12-27 with the CUDA library as the EM."""
+    from bambu_b200.quantify import bambu_quantDT
+    par = dict(unit_goldens["emParameters"], degradationBias=bias)
+    want_iters = {"estOutput_woBC": [2, 2, 11, 14, 5], "estOutput_wBC": [2, 2, 144, 395, 5]}[key]
+    for case, wi in zip(unit_goldens["cases"], want_iters):
+        det = {}
+        got = bambu_quantDT(case["input"], par, details=det)
+        exp = case["expected"][key]
+        assert got["txid"].tolist() == [int(t) for t in exp["txid"]]
+        for name in ("counts", "fullLengthCounts", "uniqueCounts"):
+            assert_same_doubles(got[name], np.array(exp[name]), f"{case['name']} {name}")
+        assert det["iters"].tolist() == [wi]
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_random_groups_exact(em, oracle_mod, seed):
+    rng = np.random.default_rng(1000 + seed)
+    a = random_arena(rng, n_groups=150, max_m=60, max_n=120)
+    check_against_oracle(em, oracle_mod, a)
+
+
+def test_larger_groups_exact(em, oracle_mod):
+    """groups that land in the bigger shared-memory classes (one CTA of 256/512 threads)"""
+    rng = np.random.default_rng(5)
+    a = random_arena(rng, n_groups=12, max_m=400, max_n=900, density=0.02, single_tx_frac=0.0)
+    b = random_arena(rng, n_groups=4, max_m=150, max_n=250, density=0.25, single_tx_frac=0.0)
+    from bambu_b200.arena import Arena
+    check_against_oracle(em, oracle_mod, Arena.concatenate([a, b]))
+
+
+def test_config2_small_exact(em, oracle_mod):
+    from bambu_b200 import synthetic
+    a = synthetic.config2(scale=0.05)
+    est, iters, _ = check_against_oracle(em, oracle_mod, a)
+    assert iters.max() > 50
+
+
+def test_config2_full_size(em, oracle_mod):
+    """BASELINE.json configs[1] at full size: 60k genes / 250k tx / 500k classes / 2M nnz.
+    The sparse oracle finishes this in seconds on the host cores, so compare
+    directly, then check the size-independent invariants of the EM."""
+    from bambu_b200 import synthetic
+    a = synthetic.config2()
+    est, iters, status = check_against_oracle(em, oracle_mod, a)
+    assert (status == 0).all()
+    M, N, _ = a.group_shapes()
+    # mass conservation per group: sum_i counts_i = sum_j K_j Y_j (every observed column is explained)
+    grp_of_row = np.repeat(np.arange(a.n_groups), M)
+    grp_of_col = np.repeat(np.arange(a.n_groups), N)
+    got = np.bincount(grp_of_row, weights=est[0], minlength=a.n_groups)
+    want = np.bincount(grp_of_col, weights=a.K * a.Y, minlength=a.n_groups)
+    assert np.allclose(got, want, rtol=1e-9)
+    assert np.all(est[1] <= est[0] * (1 + 1e-12) + 1e-12) and np.all(est[2] <= est[0] * (1 + 1e-12) + 1e-12)
+    assert np.all(est >= 0)
+
+
+def test_emWithL1_dense_entry(em, oracle_mod):
+    rng = np.random.default_rng(3)
+    for M, N in ((3, 4), (1, 5), (7, 20), (30, 64)):
+        mask = rng.random((M, N)) < 0.4
+        mask[np.arange(M), rng.integers(0, N, M)] = True
+        A = np.where(mask, rng.uniform(0.05, 1.0, (M, N)), 0.0)
+        eq = mask & (rng.random((M, N)) < 0.3)
+        multi = mask.sum(0) > 1
+        nobs = rng.integers(0, 30, N).astype(float)
+        nobs[0] += 1
+        Y, K = nobs / nobs.sum(), np.full(N, nobs.sum())
+        got = em.emWithL1(A, A * eq, A * ~multi, Y, K)
+        want, it = oracle_mod.emWithL1(A, A * eq, A * ~multi, Y, K)
+        assert got["iter"] == it
+        assert_same_doubles(got["theta"], want, f"emWithL1 {M}x{N}")
+
+
+def test_stopping_rule_parameters(em, oracle_mod):
+    rng = np.random.default_rng(11)
+    a = random_arena(rng, n_groups=40, single_tx_frac=0.0)
+    for par in ({"maxiter": 1}, {"maxiter": 2}, {"maxiter": 7}, {"conv": 1.0}, {"conv": 2.0}, {"conv": 1e-6},
+                {"conv": 0.0, "maxiter": 300}, {"minvalue": 0.5}, {"minvalue": 1e300}):
+        est, iters, status = check_against_oracle(em, oracle_mod, a, **par)
+        if par.get("maxiter", 10000) <= 7:
+            assert iters.max() <= max(par["maxiter"] - 1, 0)
+    _, iters, status = em.abundance_quantification(a, maxiter=3, conv=1e-12)
+    assert (iters == 2).all() and (status & 1).all()
+
+
+def test_nan_poisoning_group(em, oracle_mod):
+    from bambu_b200.arena import Arena
+    A = np.array([[1.0, 0.5, 0.0, 0.0], [0.0, 0.5, 1.0, 0.0], [0.0, 0.0, 0.0, 0.0]])
+    eq = np.zeros_like(A, bool)
+    eq[2, 3] = True
+    nobs = np.array([5.0, 7.0, 3.0, 2.0])
+    a = Arena.from_dense_groups([(A, eq, A.astype(bool).sum(0) > 1, nobs / nobs.sum(), np.full(4, nobs.sum()), None)])
+    est, iters, status = check_against_oracle(em, oracle_mod, a)
+    assert iters[0] == 2 and status[0] & 2 and np.isnan(est[:, 2]).all()
+
+
+def test_empty_and_degenerate_inputs(em):
+    from bambu_b200.arena import Arena
+    z = np.zeros(1, np.int64)
+    empty = Arena(z, z, z, np.zeros(0, np.int32), np.zeros(0), np.zeros(0, np.uint8), np.zeros(0), np.zeros(0),
+                  np.zeros(0, np.uint8), np.zeros(0, np.int32))
+    est, iters, status = em.abundance_quantification(empty)
+    assert est.shape == (3, 0) and len(iters) == 0
+    # a group without rows between two ordinary groups; a group whose columns are all unobserved
+    rng = np.random.default_rng(2)
+    a = random_arena(rng, n_groups=3, single_tx_frac=0.0)
+    a.grp_row_ptr = np.insert(a.grp_row_ptr, 1, a.grp_row_ptr[1])
+    a.grp_col_ptr = np.insert(a.grp_col_ptr, 1, a.grp_col_ptr[1])
+    est, iters, status = em.abundance_quantification(a)
+    assert iters[1] == 0 and np.isfinite(est).all()
+    a.Y[:] = 0.0
+    est, iters, status = em.abundance_quantification(a)
+    assert (est == 0).all() and (iters[[0, 2, 3]] == 1).all()
+
+
+def test_malformed_arena_is_rejected(em):
+    from bambu_b200 import _lib
+    rng = np.random.default_rng(4)
+    a = random_arena(rng, n_groups=5, single_tx_frac=0.0)
+    bad = a.col_idx.copy()
+    bad[3] = 10_000
+    a.col_idx = bad
+    with pytest.raises(_lib.BambuEmError) as e:
+        em.abundance_quantification(a)
+    assert e.value.code == _lib.EINVAL
+    b = random_arena(rng, n_groups=5, single_tx_frac=0.0)
+    k = int(np.nonzero(np.diff(b.row_nnz_ptr) >= 2)[0][0])
+    s = int(b.row_nnz_ptr[k])
+    b.col_idx[s], b.col_idx[s + 1] = b.col_idx[s + 1], b.col_idx[s]
+    with pytest.raises(_lib.BambuEmError) as e:
+        em.abundance_quantification(b)
+    assert e.value.code == _lib.EINVAL
+
+
+def test_plan_api_resident_runs_and_torch_buffers(em, oracle_mod):
+    import torch
+    from bambu_b200 import synthetic
+    a = synthetic.config2(scale=0.03)
+    o_est, o_it, o_st = oracle_mod.em_batched(a, mode=oracle_mod.MODE_SPARSE)
+    with em.EmPlan(a) as plan:
+        plan.upload()
+        for _ in range(2):
+            plan.run()
+            est, iters, status, nz = plan.download(want_nnz=True)
+            assert np.array_equal(iters, o_it)
+            assert_same_doubles(est, o_est, "plan est")
+            assert np.array_equal(nz, a.group_nonzeros())
+        ms = plan.last_run_ms()
+        assert ms["total_ms"] > 0 and plan.last_run_launches() >= 2 and plan.device_bytes() > a.nbytes()
+        # device buffers owned by torch, kernels ordered on torch's current stream
+        dev = torch.device("cuda:0")
+        t = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in
+             (a.col_idx, a.aval, a.nz_flags, a.Y, a.K, a.col_flags)]
+        plan.set_stream(torch.cuda.current_stream().cuda_stream)
+        plan.bind_device(*[x.data_ptr() for x in t])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        plan.run()
+        e1.record()
+        torch.cuda.synchronize()
+        assert e0.elapsed_time(e1) > 0
+        est, iters, status = plan.download()
+        assert np.array_equal(iters, o_it)
+        assert_same_doubles(est, o_est, "bound est")
