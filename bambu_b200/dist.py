@@ -1,0 +1,71 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed), static sharding,
+one gather.
+
+The EM has no cross-group term (src/em.cpp has none) and samples are independent
+(R/bambu.R:187), so the data path needs no collective: samples -- or, for a
+single sample, gene groups -- are partitioned by a work estimate, each rank runs
+its shard through the C-ABI, and the per-rank estimate tables are gathered to
+rank 0, which is what ``combineCountSes`` does with ``cbind`` in the reference
+(R/bambu_utilityFunctions.R:215-241).  NCCL is used for that gather only.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def lpt_partition(weights, n_parts):
+    """Longest-processing-time-first: heaviest item to the currently lightest
+    part.  Returns ``part_of_item`` (int array).  Deterministic (stable ties)."""
+    w = np.asarray(weights, dtype=np.float64)
+    order = np.argsort(-w, kind="stable")
+    load = np.zeros(n_parts)
+    part = np.empty(len(w), dtype=np.int64)
+    for i in order:
+        p = int(np.argmin(load))
+        part[i] = p
+        load[p] += w[i]
+    return part
+
+
+def shard_samples(sample_nnz, world):
+    """Samples -> ranks by LPT on their entry counts."""
+    part = lpt_partition(sample_nnz, world)
+    return [np.nonzero(part == r)[0] for r in range(world)]
+
+
+def shard_groups(arena, world, expected_iters=None):
+    """One sample's gene groups -> ranks by LPT on nnz x expected iterations
+    (giant loci first).  Returns, per rank, the group ids in arena order."""
+    _, _, e = arena.group_shapes()
+    w = e.astype(np.float64) * (1.0 if expected_iters is None else np.asarray(expected_iters, dtype=np.float64))
+    part = lpt_partition(w, world)
+    return [np.nonzero(part == r)[0] for r in range(world)]
+
+
+def gather_estimates(est, device=None, dst=0, group=None):
+    """Gather every rank's ``est[3, rows_r]`` (host or device tensor) to ``dst``.
+    Returns, on ``dst``, a list of host float64 arrays (one per rank, own shape);
+    ``None`` elsewhere.  Ragged shards are padded to the longest for the collective.
+    Backend-agnostic: NCCL moves device tensors, gloo (CPU tests) host tensors."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    t = est if isinstance(est, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(est))
+    on_dev = device is not None and torch.device(device).type == "cuda"
+    if on_dev:
+        t = t.to(device, non_blocking=True)
+    rows = torch.tensor([t.shape[1]], dtype=torch.int64, device=t.device)
+    all_rows = [torch.zeros_like(rows) for _ in range(world)]
+    dist.all_gather(all_rows, rows, group=group)
+    all_rows = [int(x) for x in all_rows]
+    mx = max(all_rows)
+    if t.shape[1] < mx:
+        pad = torch.zeros((3, mx), dtype=t.dtype, device=t.device)
+        pad[:, :t.shape[1]] = t
+        t = pad
+    t = t.contiguous()
+    bufs = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
+    dist.gather(t, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return [b[:, :n].cpu().numpy() for b, n in zip(bufs, all_rows)]

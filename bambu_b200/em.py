@@ -48,6 +48,23 @@ def abundance_quantification(arena: Arena, maxiter: int = 20000, conv: float = 1
     return est, iters[:n_groups], status[:n_groups]
 
 
+def abundance_quantification_into(arena: Arena, est, iters, status, maxiter=20000, conv=1e-2, minvalue=1e-8):
+    """Same call with caller-provided HOST output buffers (e.g. pinned memory):
+    ``est`` float64[3, rows], ``iters``/``status`` int32[n_groups]."""
+    L = _lib.lib()
+    g, c, r = _c(arena.grp_row_ptr, np.int64), _c(arena.grp_col_ptr, np.int64), _c(arena.row_nnz_ptr, np.int64)
+    ci, av, nf = _c(arena.col_idx, np.int32), _c(arena.aval, np.float64), _c(arena.nz_flags, np.uint8)
+    Y, K, cf = _c(arena.Y, np.float64), _c(arena.K, np.float64), _c(arena.col_flags, np.uint8)
+    n_groups, rows = len(g) - 1, int(g[-1])
+    if est.dtype != np.float64 or est.size < 3 * rows or not est.flags.c_contiguous:
+        raise ValueError("est must be a contiguous float64 buffer of 3 x rows")
+    if iters.dtype != np.int32 or status.dtype != np.int32 or iters.size < n_groups or status.size < n_groups:
+        raise ValueError("iters/status must be int32 buffers of n_groups")
+    _lib.check(L.bambu_em_batched(n_groups, _ptr(g), _ptr(c), _ptr(r), _ptr(ci), _ptr(av), _ptr(nf), _ptr(Y),
+                                  _ptr(K), _ptr(cf), int(maxiter), float(minvalue), float(conv), _ptr(est),
+                                  _ptr(iters), _ptr(status)))
+
+
 def emWithL1(A, A_full, A_unique, Y, K, maxiter: int = 10000, minvalue: float = 1e-8, conv: float = 1e-2):
     """One dense group, the signature of the reference's ``emWithL1``
     (R/RcppExports.R:12).  Returns ``{"theta": 3 x M}`` like the reference

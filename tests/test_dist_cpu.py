@@ -1,0 +1,72 @@
+"""World-size-2 gloo tests of the multi-GPU plumbing (host logic only): sharding is a
+partition, shards quantified independently reassemble to the unsharded result, and the
+gather returns every rank's table to rank 0.  The EM callable is the CPU oracle here."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as tmp
+
+from bambu_b200 import dist as bdist
+
+
+def test_lpt_partition_balances():
+    rng = np.random.default_rng(0)
+    w = rng.pareto(1.5, 500) + 1
+    part = bdist.lpt_partition(w, 8)
+    loads = np.bincount(part, weights=w, minlength=8)
+    assert sorted(np.concatenate([np.nonzero(part == r)[0] for r in range(8)]).tolist()) == list(range(500))
+    assert loads.max() <= loads.mean() + w.max()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from bambu_b200 import synthetic
+    a = synthetic.config2(scale=0.01)
+    shards = bdist.shard_groups(a, world)
+    mine = a.select_groups(shards[rank])
+    est, iters, status = oracle.em_batched(mine, mode=oracle.MODE_SPARSE)
+    got = bdist.gather_estimates(est)
+    if rank == 0:
+        full_est, full_it, _ = oracle.em_batched(a, mode=oracle.MODE_SPARSE)
+        M, _, _ = a.group_shapes()
+        ok = True
+        for r in range(world):
+            rows = np.concatenate([np.arange(a.grp_row_ptr[g], a.grp_row_ptr[g + 1]) for g in shards[r]])
+            ok &= np.array_equal(got[r], full_est[:, rows], equal_nan=True)
+        q.put(bool(ok) and len(got) == world)
+    else:
+        q.put(got is None)
+    dist.destroy_process_group()
+
+
+def test_sharded_groups_reassemble_world2():
+    world = 2
+    ctx = tmp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(res)
+
+
+def test_shard_samples_partition():
+    sh = bdist.shard_samples([5, 1, 9, 3, 3, 7, 2], 3)
+    assert sorted(np.concatenate(sh).tolist()) == list(range(7))
