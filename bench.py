@@ -206,7 +206,8 @@ def run_b200(args):
     d2h = h_est.numel() * 8 + 4 * 2 * n_groups
 
     # ---- resident plan -----------------------------------------------------------------
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()      # a real stream: the library treats the NULL stream as 'use your own'
+    torch.cuda.set_stream(stream)
     plan = EmPlan(arena)
     plan.set_stream(stream.cuda_stream)
     plan.upload_ptrs(*[pinned[n].data_ptr() for n in payload])
