@@ -32,7 +32,7 @@ SYMBOLS = {
     "bambu_em_plan_bind_device": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p]),
     "bambu_em_plan_run": (ctypes.c_int, [_p, _i32, _f64, _f64]),
     "bambu_em_plan_download": (ctypes.c_int, [_p, _p, _p, _p, _p]),
-    "bambu_em_plan_download_live": (ctypes.c_int, [_p, _p, _p]),
+    "bambu_em_plan_download_live": (ctypes.c_int, [_p, _p, _p, _p, _p]),
     "bambu_em_plan_sync": (ctypes.c_int, [_p]),
     "bambu_em_plan_device_outputs": (ctypes.c_int, [_p, ctypes.POINTER(_p), ctypes.POINTER(_p), ctypes.POINTER(_p)]),
     "bambu_em_plan_last_run_ms": (ctypes.c_int, [_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),

@@ -15,8 +15,9 @@
 
 #include "../../include/bambu_em.h"
 #include "common.cuh"
-#include "em_resident.cuh"
+#include "em_sell.cuh"
 #include "pack_kernel.cuh"
+#include "sell_kernel.cuh"
 
 using namespace bambu;
 
@@ -73,35 +74,51 @@ static int ensure_device()
 }
 
 // ------------------------------------------------------------------------------
-// size buckets
+// size classes
 // ------------------------------------------------------------------------------
-// A bucket = groups whose worst-case shared-memory footprint falls in one class.
-// The class fixes the CTA size and the dynamic shared memory of both kernels, and
-// with it how many groups are resident per SM (227 KB / footprint).
-struct BucketClass {
-    uint32_t max_bytes;   // upper bound of em_smem_bytes for the class
+// Pack buckets: groups whose WORST-CASE footprint (all columns live, no zero entries;
+// known on the host from the pointer arrays) falls in one class; the class fixes the
+// CTA size and scratch shared memory of the pack + SELL kernels.
+// EM classes: the sell kernel measures the ACTUAL shared memory a group's EM needs and
+// queues the group on the device for the EM kernel of that class; the class fixes the
+// dynamic shared memory and with it how many groups are resident per SM.
+struct PackClass {
+    uint32_t max_bytes;
     int threads;
 };
-static const BucketClass kClasses[] = {
-    {7u * 1024u, 64},     // 32 CTAs/SM (the CTA limit)
-    {14u * 1024u, 64},    // 16
-    {28u * 1024u, 128},   // 8
-    {56u * 1024u, 128},   // 4
-    {113u * 1024u, 256},  // 2
-    {kSmemMax, 512},      // 1
+static const PackClass kPackClasses[] = {
+    {14u * 1024u, 64}, {56u * 1024u, 128}, {113u * 1024u, 256}, {kSmemMax, 512},
 };
-static const int kNumClasses = (int)(sizeof(kClasses) / sizeof(kClasses[0]));
+static const int kNumPackClasses = (int)(sizeof(kPackClasses) / sizeof(kPackClasses[0]));
 
-struct Bucket {
-    int cls = 0;
+struct EmClass {
+    uint32_t max_bytes;   // dynamic shared memory of the class
+    int threads;
+};
+static const EmClass kEmClasses[kNumClasses] = {
+    {7u * 1024u, 64},      // 32 CTAs/SM (the CTA limit)
+    {14u * 1024u, 64},     // 16
+    {28u * 1024u, 128},    // 8
+    {56u * 1024u, 256},    // 4
+    {113u * 1024u, 512},   // 2
+    {kSmemMax, 1024},      // 1
+};
+
+struct Bucket {   // pack bucket
     int threads = 0;
-    uint32_t smem_em = 0, smem_pack = 0;
+    uint32_t smem_pack = 0, smem_sell = 0;
     std::vector<int32_t> work;     // group ids, largest first
     int32_t *d_work = nullptr;     // view into plan->d_work_all
-    int *d_ticket = nullptr;
-    int grid_em = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_pack0 = nullptr, ev_pack1 = nullptr, ev_em1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+struct Ctrl {   // device control block, zeroed at the start of every run
+    int err;
+    int pad;
+    unsigned long long pool_ctr;
+    int qcount[8];
+    int ticket[8];
 };
 
 struct bambu_em_plan {
@@ -117,22 +134,30 @@ struct bambu_em_plan {
     const double *d_Y = nullptr, *d_K = nullptr;
     const uint8_t *d_col_flags = nullptr;
     // device: images + outputs
-    uint8_t *d_img = nullptr;
+    uint8_t *d_img = nullptr;        // stage-1 images (compact CSR + CSC), worst-case offsets
     int64_t img_bytes = 0;
     int64_t *d_img_off = nullptr;
     PackInfo *d_info = nullptr;
+    uint8_t *d_pool = nullptr;       // SELL images, bump-allocated by the sell kernel
+    int64_t pool_bytes = 0;
+    GroupImg *d_ginfo = nullptr;
+    int32_t *d_queue = nullptr;      // kNumClasses x n_groups
     int64_t *d_nnz_nonzero = nullptr;
     double *d_est = nullptr;
     int32_t *d_iters = nullptr, *d_status = nullptr;
     int32_t *d_work_all = nullptr;
-    int *d_ctrl = nullptr;   // [0] error word, [1..] tickets
-    int n_ctrl = 0;
+    Ctrl *d_ctrl = nullptr;
     std::vector<Bucket> buckets;
     std::vector<int32_t> single_tx;   // M == 1 groups: closed form in the pack kernel only
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_fork = nullptr, ev_end = nullptr;
-    bool ran = false;
+    cudaStream_t em_stream[kNumClasses] = {};
+    cudaEvent_t em_done[kNumClasses] = {};
+    int em_grid[kNumClasses] = {};
+    cudaEvent_t ev_start = nullptr, ev_fork = nullptr, ev_packed = nullptr, ev_end = nullptr;
+    bool ran = false, finished = false;
     bool single_tx_shortcut = true;   // R/bambu-quantify_utilityFunctions.R:410-414 (run_parallel, not emWithL1)
+    int32_t last_maxiter = 0;
+    double last_minvalue = 0, last_conv = 0;
     int last_launches = 0;
     int64_t device_bytes = 0;
 };
@@ -149,44 +174,93 @@ static int dev_alloc(bambu_em_plan *p, Tp **ptr, size_t count)
 // ------------------------------------------------------------------------------
 // kernel dispatch by CTA size
 // ------------------------------------------------------------------------------
+static ClassBounds class_bounds()
+{
+    ClassBounds cb;
+    for (int c = 0; c < kNumClasses; ++c) cb.max_bytes[c] = kEmClasses[c].max_bytes;
+    return cb;
+}
+
 template <int T>
-static int launch_bucket_T(bambu_em_plan *p, Bucket &b, const ArenaDev &A, const EmParams &P)
+static int launch_pack_T(bambu_em_plan *p, Bucket &b, const ArenaDev &A)
 {
     auto pack = pack_resident_kernel<T>;
-    auto em = em_resident_kernel<T>;
+    auto sell = sell_kernel<T>;
     CUDA_TRY(cudaFuncSetAttribute(pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.smem_pack));
-    CUDA_TRY(cudaFuncSetAttribute(em, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.smem_em));
-    if (b.grid_em == 0) {
-        int per_sm = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em, T, b.smem_em));
-        if (per_sm < 1) return fail(BAMBU_EM_ECUDA, "EM kernel does not fit an SM (smem %u)", b.smem_em);
-        b.grid_em = (int)std::min<int64_t>((int64_t)b.work.size(), (int64_t)per_sm * g_num_sms);
-    }
+    CUDA_TRY(cudaFuncSetAttribute(sell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.smem_sell));
     const int n_work = (int)b.work.size();
-    CUDA_TRY(cudaEventRecord(b.ev_pack0, b.stream));
+    CUDA_TRY(cudaEventRecord(b.ev0, b.stream));
     pack<<<n_work, T, b.smem_pack, b.stream>>>(A, b.d_work, n_work, p->d_img_off, p->d_img, p->d_info,
-                                                p->d_nnz_nonzero, p->d_est, p->d_status, p->d_ctrl,
+                                                p->d_nnz_nonzero, p->d_est, p->d_status, &p->d_ctrl->err,
                                                 p->single_tx_shortcut ? 1 : 0);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(b.ev_pack1, b.stream));
-    em<<<b.grid_em, T, b.smem_em, b.stream>>>(b.d_work, n_work, b.d_ticket, p->d_img_off, p->d_img, p->d_info,
-                                              p->d_grp_row_ptr, p->total_rows, P, p->d_est, p->d_iters,
-                                              p->d_status);
+    sell<<<n_work, T, b.smem_sell, b.stream>>>(b.d_work, n_work, p->d_grp_row_ptr, p->d_img_off, p->d_img, p->d_info,
+                                                p->d_pool, (unsigned long long)p->pool_bytes, &p->d_ctrl->pool_ctr,
+                                                p->d_ginfo, class_bounds(), p->d_queue, p->n_groups,
+                                                p->d_ctrl->qcount, &p->d_ctrl->err);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(b.ev_em1, b.stream));
+    CUDA_TRY(cudaEventRecord(b.ev1, b.stream));
     p->last_launches += 2;
     return BAMBU_EM_OK;
 }
 
-static int launch_bucket(bambu_em_plan *p, Bucket &b, const ArenaDev &A, const EmParams &P)
+static int launch_pack(bambu_em_plan *p, Bucket &b, const ArenaDev &A)
 {
     switch (b.threads) {
-    case 64: return launch_bucket_T<64>(p, b, A, P);
-    case 128: return launch_bucket_T<128>(p, b, A, P);
-    case 256: return launch_bucket_T<256>(p, b, A, P);
-    case 512: return launch_bucket_T<512>(p, b, A, P);
+    case 64: return launch_pack_T<64>(p, b, A);
+    case 128: return launch_pack_T<128>(p, b, A);
+    case 256: return launch_pack_T<256>(p, b, A);
+    case 512: return launch_pack_T<512>(p, b, A);
     }
-    return fail(BAMBU_EM_EINVAL, "no kernel instance for %d threads", b.threads);
+    return fail(BAMBU_EM_EINVAL, "no pack kernel instance for %d threads", b.threads);
+}
+
+template <int T>
+static int em_config_T(int c, int *grid)
+{
+    auto em = em_sell_kernel<T>;
+    const uint32_t smem = kEmClasses[c].max_bytes;
+    CUDA_TRY(cudaFuncSetAttribute(em, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em, T, smem));
+    if (per_sm < 1) return fail(BAMBU_EM_ECUDA, "EM kernel class %d does not fit an SM", c);
+    *grid = per_sm * g_num_sms;
+    return BAMBU_EM_OK;
+}
+
+template <int T>
+static int launch_em_T(bambu_em_plan *p, int c, const EmParams &P)
+{
+    em_sell_kernel<T><<<p->em_grid[c], T, kEmClasses[c].max_bytes, p->em_stream[c]>>>(
+        p->d_queue + (int64_t)c * p->n_groups, p->d_ctrl->qcount + c, p->d_ctrl->ticket + c, p->d_ginfo, p->d_pool,
+        p->d_grp_row_ptr, p->total_rows, P, p->d_est, p->d_iters, p->d_status);
+    CUDA_TRY(cudaGetLastError());
+    p->last_launches += 1;
+    return BAMBU_EM_OK;
+}
+
+static int em_config(int c, int *grid)
+{
+    switch (kEmClasses[c].threads) {
+    case 64: return em_config_T<64>(c, grid);
+    case 128: return em_config_T<128>(c, grid);
+    case 256: return em_config_T<256>(c, grid);
+    case 512: return em_config_T<512>(c, grid);
+    case 1024: return em_config_T<1024>(c, grid);
+    }
+    return fail(BAMBU_EM_EINVAL, "no EM kernel instance for %d threads", kEmClasses[c].threads);
+}
+
+static int launch_em(bambu_em_plan *p, int c, const EmParams &P)
+{
+    switch (kEmClasses[c].threads) {
+    case 64: return launch_em_T<64>(p, c, P);
+    case 128: return launch_em_T<128>(p, c, P);
+    case 256: return launch_em_T<256>(p, c, P);
+    case 512: return launch_em_T<512>(p, c, P);
+    case 1024: return launch_em_T<1024>(p, c, P);
+    }
+    return fail(BAMBU_EM_EINVAL, "no EM kernel instance for %d threads", kEmClasses[c].threads);
 }
 
 // ------------------------------------------------------------------------------
@@ -194,7 +268,7 @@ static int launch_bucket(bambu_em_plan *p, Bucket &b, const ArenaDev &A, const E
 // ------------------------------------------------------------------------------
 extern "C" {
 
-const char *bambu_em_version(void) { return "bambu_em_b200 0.1.0 (sm_100a)"; }
+const char *bambu_em_version(void) { return "bambu_em_b200 0.2.0 (sm_100a)"; }
 const char *bambu_em_last_error(void) { return g_last_error.c_str(); }
 
 int bambu_em_device_count(void)
@@ -224,17 +298,22 @@ int bambu_em_plan_destroy(bambu_em_plan *p)
     if (p->stream) cudaStreamSynchronize(p->stream);
     for (auto &b : p->buckets) {
         if (b.stream) { cudaStreamSynchronize(b.stream); cudaStreamDestroy(b.stream); }
-        if (b.ev_pack0) cudaEventDestroy(b.ev_pack0);
-        if (b.ev_pack1) cudaEventDestroy(b.ev_pack1);
-        if (b.ev_em1) cudaEventDestroy(b.ev_em1);
+        if (b.ev0) cudaEventDestroy(b.ev0);
+        if (b.ev1) cudaEventDestroy(b.ev1);
+    }
+    for (int c = 0; c < kNumClasses; ++c) {
+        if (p->em_stream[c]) { cudaStreamSynchronize(p->em_stream[c]); cudaStreamDestroy(p->em_stream[c]); }
+        if (p->em_done[c]) cudaEventDestroy(p->em_done[c]);
     }
     if (p->ev_start) cudaEventDestroy(p->ev_start);
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_packed) cudaEventDestroy(p->ev_packed);
     if (p->ev_end) cudaEventDestroy(p->ev_end);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
     cudaFree(p->d_grp_row_ptr); cudaFree(p->d_grp_col_ptr); cudaFree(p->d_row_nnz_ptr);
     if (p->payload_owned) cudaFree(p->d_payload);
     cudaFree(p->d_img); cudaFree(p->d_img_off); cudaFree(p->d_info); cudaFree(p->d_nnz_nonzero);
+    cudaFree(p->d_pool); cudaFree(p->d_ginfo); cudaFree(p->d_queue);
     cudaFree(p->d_est); cudaFree(p->d_iters); cudaFree(p->d_status); cudaFree(p->d_work_all);
     cudaFree(p->d_ctrl);
     delete p;
@@ -263,10 +342,10 @@ static int plan_create_impl(bambu_em_plan **out, int64_t n_groups, const int64_t
         if (row_nnz_ptr[r + 1] < row_nnz_ptr[r]) { delete p; return fail(BAMBU_EM_EINVAL, "row_nnz_ptr decreases at row %lld", (long long)r); }
     p->nnz = row_nnz_ptr[p->total_rows];
 
-    // ---- classify groups, lay out the images ----------------------------------
+    // ---- classify groups by worst-case footprint, lay out the stage-1 images ------
     std::vector<int64_t> img_off((size_t)n_groups + 1, 0);
-    std::vector<std::vector<int32_t>> per_class(kNumClasses);
-    std::vector<uint32_t> ub_em((size_t)n_groups, 0), ub_pack((size_t)n_groups, 0);
+    std::vector<std::vector<int32_t>> per_class(kNumPackClasses);
+    std::vector<uint32_t> ub_pack((size_t)n_groups, 0), ub_sell((size_t)n_groups, 0);
     std::vector<int64_t> gnnz((size_t)n_groups, 0);
     int64_t off = 0;
     for (int64_t g = 0; g < n_groups; ++g) {
@@ -285,32 +364,33 @@ static int plan_create_impl(bambu_em_plan **out, int64_t n_groups, const int64_t
                         (long long)g, (long long)M, (long long)N, (long long)e);
         }
         const uint32_t bytes = em_smem_bytes((uint32_t)M, (uint32_t)N, (uint32_t)e);
-        ub_em[g] = bytes;
         ub_pack[g] = pack_smem_bytes((uint32_t)M, (uint32_t)N);
+        ub_sell[g] = sell_scratch_bytes((uint32_t)M, (uint32_t)N);
         int c = 0;
-        while (c < kNumClasses - 1 && bytes > kClasses[c].max_bytes) ++c;
+        while (c < kNumPackClasses - 1 && bytes > kPackClasses[c].max_bytes) ++c;
         per_class[c].push_back((int32_t)g);
         off += img_layout((uint32_t)M, (uint32_t)N, (uint32_t)e).total;
     }
     img_off[n_groups] = off;
     p->img_bytes = off;
+    // SELL pool: typical need is ~25 B per live entry + ~40 B per row/live column; grown on demand
+    p->pool_bytes = (int64_t)(24.0 * (double)p->nnz + 48.0 * (double)(p->total_rows + p->total_cols)) + (4 << 20);
+    p->pool_bytes = (p->pool_bytes + 15) / 16 * 16;
 
-    // single-transcript groups ride in a bucket of their own (pack kernel only)
     auto fail_destroy = [&](int code) { bambu_em_plan_destroy(p); return code; };
 #define PLAN_TRY(expr) do { int _rc = (expr); if (_rc) return fail_destroy(_rc); } while (0)
 #define PLAN_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { fail(_e == cudaErrorMemoryAllocation ? BAMBU_EM_ENOMEM : BAMBU_EM_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); return fail_destroy(_e == cudaErrorMemoryAllocation ? BAMBU_EM_ENOMEM : BAMBU_EM_ECUDA); } } while (0)
 
     size_t n_work_total = p->single_tx.size();
-    for (int c = 0; c < kNumClasses; ++c) {
+    for (int c = 0; c < kNumPackClasses; ++c) {
         if (per_class[c].empty()) continue;
         Bucket b;
-        b.cls = c;
-        b.threads = kClasses[c].threads;
+        b.threads = kPackClasses[c].threads;
         b.work = std::move(per_class[c]);
         std::stable_sort(b.work.begin(), b.work.end(), [&](int32_t x, int32_t y) { return gnnz[x] > gnnz[y]; });
         for (int32_t g : b.work) {
-            b.smem_em = std::max(b.smem_em, ub_em[g]);
             b.smem_pack = std::max(b.smem_pack, ub_pack[g]);
+            b.smem_sell = std::max(b.smem_sell, ub_sell[g]);
         }
         n_work_total += b.work.size();
         p->buckets.push_back(std::move(b));
@@ -320,21 +400,29 @@ static int plan_create_impl(bambu_em_plan **out, int64_t n_groups, const int64_t
     p->stream = p->own_stream;
     PLAN_CUDA(cudaEventCreate(&p->ev_start));
     PLAN_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    PLAN_CUDA(cudaEventCreate(&p->ev_packed));
     PLAN_CUDA(cudaEventCreate(&p->ev_end));
+    for (int c = 0; c < kNumClasses; ++c) {
+        PLAN_CUDA(cudaStreamCreateWithFlags(&p->em_stream[c], cudaStreamNonBlocking));
+        PLAN_CUDA(cudaEventCreateWithFlags(&p->em_done[c], cudaEventDisableTiming));
+        PLAN_TRY(em_config(c, &p->em_grid[c]));
+    }
 
     PLAN_TRY(dev_alloc(p, &p->d_grp_row_ptr, (size_t)n_groups + 1));
     PLAN_TRY(dev_alloc(p, &p->d_grp_col_ptr, (size_t)n_groups + 1));
     PLAN_TRY(dev_alloc(p, &p->d_row_nnz_ptr, (size_t)p->total_rows + 1));
     PLAN_TRY(dev_alloc(p, &p->d_img, (size_t)p->img_bytes));
+    PLAN_TRY(dev_alloc(p, &p->d_pool, (size_t)p->pool_bytes));
     PLAN_TRY(dev_alloc(p, &p->d_img_off, (size_t)n_groups + 1));
     PLAN_TRY(dev_alloc(p, &p->d_info, (size_t)n_groups));
+    PLAN_TRY(dev_alloc(p, &p->d_ginfo, (size_t)n_groups));
+    PLAN_TRY(dev_alloc(p, &p->d_queue, (size_t)kNumClasses * (size_t)std::max<int64_t>(n_groups, 1)));
     PLAN_TRY(dev_alloc(p, &p->d_nnz_nonzero, (size_t)n_groups));
     PLAN_TRY(dev_alloc(p, &p->d_est, (size_t)3 * p->total_rows));
     PLAN_TRY(dev_alloc(p, &p->d_iters, (size_t)n_groups));
     PLAN_TRY(dev_alloc(p, &p->d_status, (size_t)n_groups));
     PLAN_TRY(dev_alloc(p, &p->d_work_all, n_work_total));
-    p->n_ctrl = 1 + (int)p->buckets.size();
-    PLAN_TRY(dev_alloc(p, &p->d_ctrl, (size_t)p->n_ctrl));
+    PLAN_TRY(dev_alloc(p, &p->d_ctrl, 1));
 
     cudaStream_t s = p->stream;
     PLAN_CUDA(cudaMemcpyAsync(p->d_grp_row_ptr, grp_row_ptr, sizeof(int64_t) * (n_groups + 1), cudaMemcpyHostToDevice, s));
@@ -342,16 +430,13 @@ static int plan_create_impl(bambu_em_plan **out, int64_t n_groups, const int64_t
     PLAN_CUDA(cudaMemcpyAsync(p->d_row_nnz_ptr, row_nnz_ptr, sizeof(int64_t) * (p->total_rows + 1), cudaMemcpyHostToDevice, s));
     PLAN_CUDA(cudaMemcpyAsync(p->d_img_off, img_off.data(), sizeof(int64_t) * (n_groups + 1), cudaMemcpyHostToDevice, s));
     size_t woff = 0;
-    int bi = 0;
     for (auto &b : p->buckets) {
         b.d_work = p->d_work_all + woff;
-        b.d_ticket = p->d_ctrl + 1 + bi++;
         PLAN_CUDA(cudaMemcpyAsync(b.d_work, b.work.data(), sizeof(int32_t) * b.work.size(), cudaMemcpyHostToDevice, s));
         woff += b.work.size();
         PLAN_CUDA(cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
-        PLAN_CUDA(cudaEventCreate(&b.ev_pack0));
-        PLAN_CUDA(cudaEventCreate(&b.ev_pack1));
-        PLAN_CUDA(cudaEventCreate(&b.ev_em1));
+        PLAN_CUDA(cudaEventCreate(&b.ev0));
+        PLAN_CUDA(cudaEventCreate(&b.ev1));
     }
     if (!p->single_tx.empty())
         PLAN_CUDA(cudaMemcpyAsync(p->d_work_all + woff, p->single_tx.data(), sizeof(int32_t) * p->single_tx.size(), cudaMemcpyHostToDevice, s));
@@ -427,17 +512,12 @@ int bambu_em_plan_bind_device(bambu_em_plan *p, const int32_t *d_col_idx, const 
     return BAMBU_EM_OK;
 }
 
-int bambu_em_plan_run(bambu_em_plan *p, int32_t maxiter, double minvalue, double conv)
+static int enqueue_run(bambu_em_plan *p)
 {
-    if (!p) return fail(BAMBU_EM_EINVAL, "plan is NULL");
-    if (!p->payload_ready) return fail(BAMBU_EM_ESTATE, "run before upload/bind_device");
-    if (conv != conv || minvalue != minvalue) return fail(BAMBU_EM_EINVAL, "conv/minvalue is NaN");
-    int rc = ensure_device();
-    if (rc) return rc;
-
     EmParams P;
-    P.maxiter = maxiter;
-    P.minvalue = minvalue;
+    const double conv = p->last_conv;
+    P.maxiter = p->last_maxiter;
+    P.minvalue = p->last_minvalue;
     P.conv = conv;
     if (conv > 1e-290 && std::isfinite(conv)) {
         P.conv_hi = conv * (1.0 + std::ldexp(1.0, -40));
@@ -453,51 +533,92 @@ int bambu_em_plan_run(bambu_em_plan *p, int32_t maxiter, double minvalue, double
     A.n_groups = p->n_groups; A.total_rows = p->total_rows;
 
     cudaStream_t s = p->stream;
+    const int64_t ng = std::max<int64_t>(p->n_groups, 1);
     p->last_launches = 0;
     CUDA_TRY(cudaEventRecord(p->ev_start, s));
-    CUDA_TRY(cudaMemsetAsync(p->d_ctrl, 0, sizeof(int) * p->n_ctrl, s));
-    CUDA_TRY(cudaMemsetAsync(p->d_iters, 0, sizeof(int32_t) * std::max<int64_t>(p->n_groups, 1), s));
-    CUDA_TRY(cudaMemsetAsync(p->d_status, 0, sizeof(int32_t) * std::max<int64_t>(p->n_groups, 1), s));
+    CUDA_TRY(cudaMemsetAsync(p->d_ctrl, 0, sizeof(Ctrl), s));
+    CUDA_TRY(cudaMemsetAsync(p->d_iters, 0, sizeof(int32_t) * ng, s));
+    CUDA_TRY(cudaMemsetAsync(p->d_status, 0, sizeof(int32_t) * ng, s));
     CUDA_TRY(cudaMemsetAsync(p->d_est, 0, sizeof(double) * std::max<int64_t>(3 * p->total_rows, 1), s));
-    CUDA_TRY(cudaMemsetAsync(p->d_info, 0, sizeof(PackInfo) * std::max<int64_t>(p->n_groups, 1), s));
-    CUDA_TRY(cudaMemsetAsync(p->d_nnz_nonzero, 0, sizeof(int64_t) * std::max<int64_t>(p->n_groups, 1), s));
+    CUDA_TRY(cudaMemsetAsync(p->d_info, 0, sizeof(PackInfo) * ng, s));
+    CUDA_TRY(cudaMemsetAsync(p->d_ginfo, 0, sizeof(GroupImg) * ng, s));
+    CUDA_TRY(cudaMemsetAsync(p->d_nnz_nonzero, 0, sizeof(int64_t) * ng, s));
     CUDA_TRY(cudaEventRecord(p->ev_fork, s));
+    // pack + SELL, one bucket per stream
     for (auto &b : p->buckets) {
         CUDA_TRY(cudaStreamWaitEvent(b.stream, p->ev_fork, 0));
-        rc = launch_bucket(p, b, A, P);
+        int rc = launch_pack(p, b, A);
         if (rc) return rc;
-        CUDA_TRY(cudaStreamWaitEvent(s, b.ev_em1, 0));
+        CUDA_TRY(cudaStreamWaitEvent(s, b.ev1, 0));
     }
     if (!p->single_tx.empty()) {
         size_t woff = 0;
         for (auto &b : p->buckets) woff += b.work.size();
         const int n = (int)p->single_tx.size();
         pack_resident_kernel<64><<<n, 64, 0, s>>>(A, p->d_work_all + woff, n, p->d_img_off, p->d_img, p->d_info,
-                                                   p->d_nnz_nonzero, p->d_est, p->d_status, p->d_ctrl, 1);
+                                                   p->d_nnz_nonzero, p->d_est, p->d_status, &p->d_ctrl->err, 1);
         CUDA_TRY(cudaGetLastError());
         p->last_launches += 1;
     }
+    CUDA_TRY(cudaEventRecord(p->ev_packed, s));
+    // EM, one class per stream; the queues were filled on the device
+    if (!p->buckets.empty()) {
+        for (int c = kNumClasses - 1; c >= 0; --c) {
+            CUDA_TRY(cudaStreamWaitEvent(p->em_stream[c], p->ev_packed, 0));
+            int rc = launch_em(p, c, P);
+            if (rc) return rc;
+            CUDA_TRY(cudaEventRecord(p->em_done[c], p->em_stream[c]));
+            CUDA_TRY(cudaStreamWaitEvent(s, p->em_done[c], 0));
+        }
+    }
     CUDA_TRY(cudaEventRecord(p->ev_end, s));
     p->ran = true;
+    p->finished = false;
     return BAMBU_EM_OK;
 }
 
-static int check_device_error(bambu_em_plan *p)
+int bambu_em_plan_run(bambu_em_plan *p, int32_t maxiter, double minvalue, double conv)
 {
-    int err = 0;
-    CUDA_TRY(cudaMemcpyAsync(&err, p->d_ctrl, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
-    CUDA_TRY(cudaStreamSynchronize(p->stream));
-    if (err == kErrColRange) return fail(BAMBU_EM_EINVAL, "col_idx outside its group's column range");
-    if (err == kErrColOrder) return fail(BAMBU_EM_EINVAL, "col_idx not strictly increasing inside a row");
-    if (err) return fail(BAMBU_EM_ECUDA, "device error word %d", err);
-    return BAMBU_EM_OK;
+    if (!p) return fail(BAMBU_EM_EINVAL, "plan is NULL");
+    if (!p->payload_ready) return fail(BAMBU_EM_ESTATE, "run before upload/bind_device");
+    if (conv != conv || minvalue != minvalue) return fail(BAMBU_EM_EINVAL, "conv/minvalue is NaN");
+    int rc = ensure_device();
+    if (rc) return rc;
+    p->last_maxiter = maxiter;
+    p->last_minvalue = minvalue;
+    p->last_conv = conv;
+    return enqueue_run(p);
+}
+
+// wait for the run; if the SELL pool was too small, grow it and run again
+static int finish_run(bambu_em_plan *p)
+{
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        int err = 0;
+        CUDA_TRY(cudaMemcpyAsync(&err, &p->d_ctrl->err, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        CUDA_TRY(cudaStreamSynchronize(p->stream));
+        if (err == 0) { p->finished = true; return BAMBU_EM_OK; }
+        if (err == kErrColRange) return fail(BAMBU_EM_EINVAL, "col_idx outside its group's column range");
+        if (err == kErrColOrder) return fail(BAMBU_EM_EINVAL, "col_idx not strictly increasing inside a row");
+        if (err == kErrTooBig) return fail(BAMBU_EM_EINVAL, "a gene group's image exceeds the shared-memory resident tier");
+        if (err != kErrPool) return fail(BAMBU_EM_ECUDA, "device error word %d", err);
+        cudaFree(p->d_pool);
+        p->d_pool = nullptr;
+        p->device_bytes -= p->pool_bytes;
+        p->pool_bytes *= 2;
+        int rc = dev_alloc(p, &p->d_pool, (size_t)p->pool_bytes);
+        if (rc) return rc;
+        rc = enqueue_run(p);
+        if (rc) return rc;
+    }
+    return fail(BAMBU_EM_ENOMEM, "SELL image pool kept overflowing");
 }
 
 int bambu_em_plan_sync(bambu_em_plan *p)
 {
     if (!p) return fail(BAMBU_EM_EINVAL, "plan is NULL");
+    if (p->ran && !p->finished) return finish_run(p);
     CUDA_TRY(cudaStreamSynchronize(p->stream));
-    if (p->ran) return check_device_error(p);
     return BAMBU_EM_OK;
 }
 
@@ -505,6 +626,7 @@ int bambu_em_plan_download(bambu_em_plan *p, double *est, int32_t *iters, int32_
 {
     if (!p) return fail(BAMBU_EM_EINVAL, "plan is NULL");
     if (!p->ran) return fail(BAMBU_EM_ESTATE, "download before run");
+    if (!p->finished) { int rc = finish_run(p); if (rc) return rc; }
     cudaStream_t s = p->stream;
     if (est && p->total_rows)
         CUDA_TRY(cudaMemcpyAsync(est, p->d_est, sizeof(double) * 3 * p->total_rows, cudaMemcpyDeviceToHost, s));
@@ -514,21 +636,28 @@ int bambu_em_plan_download(bambu_em_plan *p, double *est, int32_t *iters, int32_
         CUDA_TRY(cudaMemcpyAsync(status, p->d_status, sizeof(int32_t) * p->n_groups, cudaMemcpyDeviceToHost, s));
     if (nnz_nonzero && p->n_groups)
         CUDA_TRY(cudaMemcpyAsync(nnz_nonzero, p->d_nnz_nonzero, sizeof(int64_t) * p->n_groups, cudaMemcpyDeviceToHost, s));
-    return check_device_error(p);
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return BAMBU_EM_OK;
 }
 
-int bambu_em_plan_download_live(bambu_em_plan *p, int32_t *live_cols, int32_t *live_nnz)
+int bambu_em_plan_download_live(bambu_em_plan *p, int32_t *live_cols, int32_t *live_nnz, int32_t *smem_bytes,
+                                int32_t *slots)
 {
     if (!p) return fail(BAMBU_EM_EINVAL, "plan is NULL");
     if (!p->ran) return fail(BAMBU_EM_ESTATE, "download before run");
+    if (!p->finished) { int rc = finish_run(p); if (rc) return rc; }
     std::vector<PackInfo> h((size_t)p->n_groups);
+    std::vector<GroupImg> gi((size_t)p->n_groups);
     if (p->n_groups) {
         CUDA_TRY(cudaMemcpyAsync(h.data(), p->d_info, sizeof(PackInfo) * p->n_groups, cudaMemcpyDeviceToHost, p->stream));
+        CUDA_TRY(cudaMemcpyAsync(gi.data(), p->d_ginfo, sizeof(GroupImg) * p->n_groups, cudaMemcpyDeviceToHost, p->stream));
         CUDA_TRY(cudaStreamSynchronize(p->stream));
     }
     for (int64_t g = 0; g < p->n_groups; ++g) {
         if (live_cols) live_cols[g] = h[g].NL;
         if (live_nnz) live_nnz[g] = h[g].nnzL;
+        if (smem_bytes) smem_bytes[g] = (int32_t)gi[g].smem_bytes;
+        if (slots) slots[g] = (int32_t)(gi[g].slotsR + gi[g].slotsC);
     }
     return BAMBU_EM_OK;
 }
@@ -546,16 +675,11 @@ int bambu_em_plan_last_run_ms(bambu_em_plan *p, float *pack_ms, float *em_ms, fl
 {
     if (!p) return fail(BAMBU_EM_EINVAL, "plan is NULL");
     if (!p->ran) return fail(BAMBU_EM_ESTATE, "no run yet");
+    if (!p->finished) { int rc = finish_run(p); if (rc) return rc; }
     CUDA_TRY(cudaEventSynchronize(p->ev_end));
     float pk = 0.f, em = 0.f, tot = 0.f;
-    for (auto &b : p->buckets) {
-        float a = 0.f, c = 0.f;
-        CUDA_TRY(cudaEventSynchronize(b.ev_em1));
-        CUDA_TRY(cudaEventElapsedTime(&a, b.ev_pack0, b.ev_pack1));
-        CUDA_TRY(cudaEventElapsedTime(&c, b.ev_pack1, b.ev_em1));
-        pk += a;
-        em += c;
-    }
+    CUDA_TRY(cudaEventElapsedTime(&pk, p->ev_start, p->ev_packed));
+    CUDA_TRY(cudaEventElapsedTime(&em, p->ev_packed, p->ev_end));
     CUDA_TRY(cudaEventElapsedTime(&tot, p->ev_start, p->ev_end));
     if (pack_ms) *pack_ms = pk;
     if (em_ms) *em_ms = em;

@@ -78,12 +78,80 @@ __host__ __device__ inline uint32_t pack_smem_bytes(uint32_t M, uint32_t N)
     return 4u * (N + (M + 1) + (N + 1) + N);
 }
 
+// ---- SELL image: what the EM kernel iterates on -----------------------------------
+// Every line (a row for the M-phase, a live column for the E-phase) is split into
+// its even-position and odd-position entries -- the two accumulators of arma::sum --
+// each kept in ascending index order.  Slot k of a line holds its k-th even and k-th
+// odd entry, so a line needs L = max(#even, #odd) slots; missing entries are padded
+// with (value 0.0, index of a dummy vector element that is always 0.0), which adds an
+// exact +0.0.  Lines are ordered by L (descending) and cut into slices of 32 -- one
+// warp -- padded to the slice's longest line; inside a slice storage is slot-major,
+// lane-minor, so that a warp reads 32 consecutive values (no bank conflicts) and runs
+// a loop whose trip count is uniform (no divergence, no parity branch).
+//
+//   [rs f64 M][Yl f64 NL]
+//   [row side : slotsR x {valE f64 x32 | valO f64 x32 | idxE u16 x32 | idxO u16 x32}]   640 B / slot
+//   [col side : slotsC x {same}]
+//   [rowid u16 32*nSliceR][colid u16 32*nSliceC][startR u32 nSliceR+1][startC u32 nSliceC+1]
+//                                                                   <- copied to shared memory
+//   [KY f64 NL][cm u8 NL+1][eq u8 : slotsR x {E x32 | O x32}]        <- read once, in the epilogue
+struct GroupImg {
+    uint32_t off16;       // image offset inside the pool, in 16-byte units
+    uint32_t smem_bytes;  // shared memory the EM kernel needs; 0 = not queued
+    uint16_t M, NL;
+    uint16_t nSliceR, nSliceC;
+    uint32_t slotsR, slotsC;
+    uint32_t nnzL;
+    int32_t cls;
+};
+static_assert(sizeof(GroupImg) == 32, "GroupImg layout");
+
+constexpr uint32_t kSlotBytes = 640;
+
+struct SellLayout {
+    uint32_t rs, Yl, sideR, sideC, rowid, colid, startR, startC, copy_bytes, KY, cm, eq, total;
+};
+
+__host__ __device__ inline SellLayout sell_layout(uint32_t M, uint32_t NL, uint32_t nSliceR, uint32_t nSliceC,
+                                                  uint32_t slotsR, uint32_t slotsC)
+{
+    SellLayout L;
+    L.rs = 0;
+    L.Yl = 8u * M;
+    L.sideR = L.Yl + 8u * NL;
+    L.sideC = L.sideR + kSlotBytes * slotsR;
+    L.rowid = L.sideC + kSlotBytes * slotsC;
+    L.colid = L.rowid + 64u * nSliceR;
+    L.startR = L.colid + 64u * nSliceC;
+    L.startC = L.startR + 4u * (nSliceR + 1);
+    L.copy_bytes = align_up(L.startC + 4u * (nSliceC + 1), 16);
+    L.KY = L.copy_bytes;
+    L.cm = L.KY + 8u * NL;
+    L.eq = align_up(L.cm + NL + 1, 16);
+    L.total = align_up(L.eq + 64u * slotsR, 16);
+    return L;
+}
+
+__host__ __device__ inline uint32_t sell_smem_bytes(const SellLayout &L, uint32_t M, uint32_t NL)
+{
+    return L.copy_bytes + 8u * (M + 1) + 8u * (NL + 1);
+}
+
+// shared-memory scratch of the SELL builder for a group (lengths, ids, slice starts, histogram)
+__host__ __device__ inline uint32_t sell_scratch_bytes(uint32_t M, uint32_t N)
+{
+    return 4u * 1026u + 2u * (M + N) + 2u * (M + N + 64u) + 4u * ((M + 31) / 32 + (N + 31) / 32 + 4u) + 64u;
+}
+
+constexpr int kNumClasses = 6;
 constexpr uint32_t kSmemMax = 227u * 1024u - 256u;  // per-CTA opt-in maximum minus static shared
 constexpr int kMaxIndex = 32767;                    // u16 index carries a parity bit
 
 // error codes written to the device error word by the kernels
 constexpr int kErrColRange = 1;   // col_idx outside [0, N)
 constexpr int kErrColOrder = 2;   // col_idx not strictly increasing inside a row
+constexpr int kErrPool = 3;       // image pool exhausted (the host grows it and reruns)
+constexpr int kErrTooBig = 4;     // a group's SELL image exceeds shared memory
 
 // ---- block-wide exclusive scan, in place, n arbitrary ---------------------------
 template <int T>

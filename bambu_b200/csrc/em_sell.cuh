@@ -1,0 +1,248 @@
+// em_sell.cuh -- the EM of one gene group on its SELL image, resident in shared memory.
+//
+// Restates exactly the arithmetic of
+//   em_theta   src/em.cpp:9-71     (fixed point on theta, group-level stopping rule)
+//   emWithL1   src/em.cpp:77-110   (baseSum and the three weighted row sums)
+// Every reduction adds its terms in increasing dense-index order into Armadillo's two
+// interleaved accumulators (even position -> acc1, odd -> acc2, result acc1 + acc2):
+// the SELL image keeps the two streams apart, so a lane runs two independent add
+// chains with no parity test, and a warp's loop trip count is uniform.  One lane owns
+// one live column in the E-phase and one row in the M-phase; a warp owns slices of 32;
+// a CTA owns one group at a time and pulls groups from its class's queue.
+//
+// FP64 throughout; products and sums use the non-contracting intrinsics: the reference
+// rounds a_ij*theta_i before it is summed (src/em.cpp:46-47), so no FMA may be formed.
+#pragma once
+#include "common.cuh"
+
+namespace bambu {
+
+struct EmParams {
+    int32_t maxiter;
+    double minvalue, conv;
+    double conv_lo, conv_hi;  // conv*(1 -+ 2^-40): division-free screen of |d|/theta > conv
+};
+
+__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000ll); }
+
+// sum over one line of a SELL side: a1 = even stream, a2 = odd stream.
+// MODE 0: plain; MODE 1: also count gathered elements that are not finite.
+template <int MODE>
+__device__ __forceinline__ void line_sums(const uint8_t *__restrict__ side, uint32_t s0, uint32_t s1, int lane,
+                                          const double *__restrict__ vec, double &a1, double &a2, int &cnt)
+{
+    const uint8_t *p = side + (size_t)kSlotBytes * s0;
+#pragma unroll 2
+    for (uint32_t s = s0; s < s1; ++s, p += kSlotBytes) {
+        const double ve = reinterpret_cast<const double *>(p)[lane];
+        const double vo = reinterpret_cast<const double *>(p + 256)[lane];
+        const uint32_t ie = reinterpret_cast<const uint16_t *>(p + 512)[lane];
+        const uint32_t io = reinterpret_cast<const uint16_t *>(p + 576)[lane];
+        const double xe = vec[ie], xo = vec[io];
+        if (MODE == 1) cnt += (!is_finite(xe)) + (!is_finite(xo));
+        a1 = __dadd_rn(a1, __dmul_rn(ve, xe));
+        a2 = __dadd_rn(a2, __dmul_rn(vo, xo));
+    }
+}
+
+template <int T>
+__global__ void __launch_bounds__(T)
+em_sell_kernel(const int32_t *__restrict__ queue, const int *__restrict__ qcount, int *__restrict__ ticket,
+               const GroupImg *__restrict__ ginfo, const uint8_t *__restrict__ pool,
+               const int64_t *__restrict__ grp_row_ptr, int64_t total_rows, EmParams P,
+               double *__restrict__ est, int32_t *__restrict__ iters, int32_t *__restrict__ status)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ int s_next;
+    __shared__ int s_nf[2];    // rows whose theta is non-finite, written by M-phase `it` into [it&1]
+    __shared__ int s_rbad[2];  // a ratio Y/c of E-phase `it` is non-finite, [it&1]
+    __shared__ int s_Q;        // columns whose baseSum is +-inf (epilogue)
+
+    constexpr int NW = T / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_work = *qcount;
+    for (;;) {
+        if (tid == 0) s_next = atomicAdd(ticket, 1);
+        __syncthreads();
+        const int w = s_next;
+        if (w >= n_work) break;
+        const int g = queue[w];
+        const GroupImg gi = ginfo[g];
+        const int M = gi.M, NL = gi.NL, nSliceR = gi.nSliceR, nSliceC = gi.nSliceC;
+        const SellLayout L = sell_layout(gi.M, gi.NL, gi.nSliceR, gi.nSliceC, gi.slotsR, gi.slotsC);
+        const uint8_t *gimg = pool + ((size_t)gi.off16 << 4);
+        const int64_t row0 = grp_row_ptr[g];
+
+        // ---- image -> shared memory ------------------------------------------------
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(gimg);
+            uint4 *dst = reinterpret_cast<uint4 *>(smem);
+            const int n16 = (int)(L.copy_bytes >> 4);
+            for (int i = tid; i < n16; i += T) dst[i] = __ldg(src + i);
+        }
+        const double *rs = reinterpret_cast<const double *>(smem + L.rs);
+        const double *Yl = reinterpret_cast<const double *>(smem + L.Yl);
+        const uint8_t *sideR = smem + L.sideR;
+        const uint8_t *sideC = smem + L.sideC;
+        const uint16_t *rowid = reinterpret_cast<const uint16_t *>(smem + L.rowid);
+        const uint16_t *colid = reinterpret_cast<const uint16_t *>(smem + L.colid);
+        const uint32_t *startR = reinterpret_cast<const uint32_t *>(smem + L.startR);
+        const uint32_t *startC = reinterpret_cast<const uint32_t *>(smem + L.startC);
+        double *theta = reinterpret_cast<double *>(smem + L.copy_bytes);   // M + 1, theta[M] = 0 (padding target)
+        double *ratio = theta + (M + 1);                                    // NL + 1, ratio[NL] = 0
+        for (int i = tid; i < M; i += T) theta[i] = 1.0;                    // src/em.cpp:20-21
+        if (tid == 0) {
+            theta[M] = 0.0;
+            ratio[NL] = 0.0;
+            s_nf[0] = s_nf[1] = 0; s_rbad[0] = s_rbad[1] = 0; s_Q = 0;
+        }
+        __syncthreads();
+
+        // ---- em_theta: while (delta > conv && iter < maxiter-1)  src/em.cpp:42 --------
+        int iter = 0;
+        bool over = (1.0 > P.conv);   // delta starts at 1 (src/em.cpp:38)
+        while (over && iter < P.maxiter - 1) {
+            ++iter;
+            const int par = iter & 1;
+            const int nP = s_nf[par ^ 1];          // non-finite thetas entering this update
+            if (tid == 0) s_nf[par] = 0;
+            // E-phase: c_j = sum_i a_ij*theta_i (:46-47), ratio_j = Y_j / c_j (:48)
+            for (int sl = warp; sl < nSliceC; sl += NW) {
+                const int j = colid[sl * 32 + lane];
+                double a1 = 0.0, a2 = 0.0;
+                int cnt = 0;
+                if (nP == 0) {
+                    line_sums<0>(sideC, startC[sl], startC[sl + 1], lane, theta, a1, a2, cnt);
+                } else {
+                    // dense semantics: a row with non-finite theta poisons every column it has a
+                    // structural zero in (0*NaN), SURVEY Appendix C.14
+                    line_sums<1>(sideC, startC[sl], startC[sl + 1], lane, theta, a1, a2, cnt);
+                    if (cnt < nP) a1 = qnan();
+                }
+                if (j < NL) {
+                    const double r = __ddiv_rn(Yl[j], __dadd_rn(a1, a2));
+                    ratio[j] = r;
+                    if (!is_finite(r)) s_rbad[par] = 1;
+                }
+            }
+            __syncthreads();
+            // M-phase: theta_i = sum_j (a_ij*theta_i)*ratio_j / rs_i, NaN terms -> 0 (:48-50)
+            const bool hazard = (s_rbad[par] != 0) || (nP != 0);
+            if (tid == 0) s_rbad[par ^ 1] = 0;
+            int flag = (P.conv < 0.0) ? 1 : 0;   // delta >= 0 > conv whenever conv is negative
+            for (int sl = warp; sl < nSliceR; sl += NW) {
+                const int i = rowid[sl * 32 + lane];
+                const double th = theta[i];      // i == M on padding lanes: 0.0
+                double a1 = 0.0, a2 = 0.0;
+                const uint8_t *p = sideR + (size_t)kSlotBytes * startR[sl];
+                const uint32_t ns = startR[sl + 1] - startR[sl];
+                if (!hazard) {
+#pragma unroll 2
+                    for (uint32_t s = 0; s < ns; ++s, p += kSlotBytes) {
+                        const double ve = reinterpret_cast<const double *>(p)[lane];
+                        const double vo = reinterpret_cast<const double *>(p + 256)[lane];
+                        const uint32_t ie = reinterpret_cast<const uint16_t *>(p + 512)[lane];
+                        const uint32_t io = reinterpret_cast<const uint16_t *>(p + 576)[lane];
+                        a1 = __dadd_rn(a1, __dmul_rn(__dmul_rn(ve, th), ratio[ie]));
+                        a2 = __dadd_rn(a2, __dmul_rn(__dmul_rn(vo, th), ratio[io]));
+                    }
+                } else {
+                    for (uint32_t s = 0; s < ns; ++s, p += kSlotBytes) {
+                        const double ve = reinterpret_cast<const double *>(p)[lane];
+                        const double vo = reinterpret_cast<const double *>(p + 256)[lane];
+                        const uint32_t ie = reinterpret_cast<const uint16_t *>(p + 512)[lane];
+                        const uint32_t io = reinterpret_cast<const uint16_t *>(p + 576)[lane];
+                        double te = __dmul_rn(__dmul_rn(ve, th), ratio[ie]);
+                        double to = __dmul_rn(__dmul_rn(vo, th), ratio[io]);
+                        if (te != te) te = 0.0;   // replace(nan, 0)  (:49)
+                        if (to != to) to = 0.0;
+                        a1 = __dadd_rn(a1, te);
+                        a2 = __dadd_rn(a2, to);
+                    }
+                }
+                if (i < M) {
+                    const double after = __ddiv_rn(__dadd_rn(a1, a2), rs[i]);
+                    theta[i] = after;
+                    if (!is_finite(after)) atomicAdd(&s_nf[par], 1);
+                    // delta = max over {after > minvalue} of |after-before|/after  (:54-63); only
+                    // "delta > conv" is needed: screen without the division, divide only inside
+                    // the 2^-40 band around conv
+                    if (after > P.minvalue) {
+                        const double diff = fabs(__dadd_rn(after, -th));
+                        if (diff > __dmul_rn(after, P.conv_hi)) flag = 1;
+                        else if (diff >= __dmul_rn(after, P.conv_lo)) {
+                            if (__ddiv_rn(diff, after) > P.conv) flag = 1;
+                        }
+                    }
+                }
+            }
+            over = __syncthreads_or(flag) != 0;
+        }
+
+        // ---- emWithL1 epilogue: src/em.cpp:97-102 -------------------------------------
+        const int nP = (iter == 0) ? 0 : s_nf[iter & 1];
+        const double *KY = reinterpret_cast<const double *>(gimg + L.KY);
+        const uint8_t *cm = gimg + L.cm;
+        const uint8_t *eq = gimg + L.eq;
+        for (int sl = warp; sl < nSliceC; sl += NW) {
+            const int j = colid[sl * 32 + lane];
+            double a1 = 0.0, a2 = 0.0;
+            int cnt = 0;
+            line_sums<1>(sideC, startC[sl], startC[sl + 1], lane, theta, a1, a2, cnt);
+            if (j < NL) {
+                double c = __dadd_rn(a1, a2);
+                if (cnt < nP) c = qnan();
+                double b = __ddiv_rn(__ldg(KY + j), c);   // (K % Y) / colsum  (:98)
+                if (b != b) b = 0.0;                      // replace(nan, 0)   (:99)
+                ratio[j] = b;
+                if (fabs(b) > 1.7976931348623157e308) atomicAdd(&s_Q, 1);
+            }
+        }
+        __syncthreads();
+        const int Q = s_Q;
+        int bad = 0;
+        for (int sl = warp; sl < nSliceR; sl += NW) {
+            const int i = rowid[sl * 32 + lane];
+            const double th = theta[i];
+            double t1 = 0, t2 = 0, f1 = 0, f2 = 0, u1 = 0, u2 = 0;
+            int cnt = 0;
+            const uint32_t s0 = startR[sl], s1 = startR[sl + 1];
+            const uint8_t *p = sideR + (size_t)kSlotBytes * s0;
+            for (uint32_t s = s0; s < s1; ++s, p += kSlotBytes) {
+                const double ve = reinterpret_cast<const double *>(p)[lane];
+                const double vo = reinterpret_cast<const double *>(p + 256)[lane];
+                const uint32_t ie = reinterpret_cast<const uint16_t *>(p + 512)[lane];
+                const uint32_t io = reinterpret_cast<const uint16_t *>(p + 576)[lane];
+                const double be = ratio[ie], bo = ratio[io];
+                const double fe = __ldg(eq + (size_t)64 * s + lane) ? ve : __dmul_rn(ve, 0.0);        // fullAval = aval*equal
+                const double fo = __ldg(eq + (size_t)64 * s + 32 + lane) ? vo : __dmul_rn(vo, 0.0);
+                const double ue = __ldg(cm + ie) ? __dmul_rn(ve, 0.0) : ve;                            // uniqueAval = aval*!multi
+                const double uo = __ldg(cm + io) ? __dmul_rn(vo, 0.0) : vo;
+                cnt += (fabs(be) > 1.7976931348623157e308) + (fabs(bo) > 1.7976931348623157e308);
+                t1 = __dadd_rn(t1, __dmul_rn(__dmul_rn(ve, th), be));
+                t2 = __dadd_rn(t2, __dmul_rn(__dmul_rn(vo, th), bo));
+                f1 = __dadd_rn(f1, __dmul_rn(__dmul_rn(fe, th), be));
+                f2 = __dadd_rn(f2, __dmul_rn(__dmul_rn(fo, th), bo));
+                u1 = __dadd_rn(u1, __dmul_rn(__dmul_rn(ue, th), be));
+                u2 = __dadd_rn(u2, __dmul_rn(__dmul_rn(uo, th), bo));
+            }
+            if (i < M) {
+                double e0 = __dadd_rn(t1, t2), e1 = __dadd_rn(f1, f2), e2 = __dadd_rn(u1, u2);
+                // dense 0*NaN / 0*Inf at the structural zeros of this row
+                if (!is_finite(th) || cnt < Q) e0 = e1 = e2 = qnan();
+                est[row0 + i] = e0;
+                est[total_rows + row0 + i] = e1;
+                est[2 * total_rows + row0 + i] = e2;
+                bad |= !(is_finite(e0) && is_finite(e1) && is_finite(e2));
+            }
+        }
+        const int anybad = __syncthreads_or(bad);
+        if (tid == 0) {
+            iters[g] = iter;
+            status[g] = ((iter >= P.maxiter - 1 && over) ? 1 : 0) | (anybad ? 2 : 0);
+        }
+        // the barrier above also protects shared memory against the next group's load
+    }
+}
+
+}  // namespace bambu

@@ -148,8 +148,15 @@ class EmPlan:
         """(live columns, live entries) per group, as kept by the pack kernels."""
         nl = np.zeros(max(self.n_groups, 1), dtype=np.int32)
         nz = np.zeros(max(self.n_groups, 1), dtype=np.int32)
-        _lib.check(self._L.bambu_em_plan_download_live(self._h, _ptr(nl), _ptr(nz)))
+        _lib.check(self._L.bambu_em_plan_download_live(self._h, _ptr(nl), _ptr(nz), None, None))
         return nl[:self.n_groups], nz[:self.n_groups]
+
+    def download_image_stats(self):
+        """(shared-memory bytes of the EM, 32-lane slots) per group."""
+        sm = np.zeros(max(self.n_groups, 1), dtype=np.int32)
+        sl = np.zeros(max(self.n_groups, 1), dtype=np.int32)
+        _lib.check(self._L.bambu_em_plan_download_live(self._h, None, None, _ptr(sm), _ptr(sl)))
+        return sm[:self.n_groups], sl[:self.n_groups]
 
     def download_ptrs(self, est, iters, status):
         _lib.check(self._L.bambu_em_plan_download(self._h, ctypes.c_void_p(int(est)), ctypes.c_void_p(int(iters)),

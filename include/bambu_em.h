@@ -131,15 +131,19 @@ int bambu_em_plan_run(bambu_em_plan *plan, int32_t maxiter, double minvalue, dou
  * the number of entries with aval != 0 (the nnz_g of the nnz-iterations metric). */
 int bambu_em_plan_download(bambu_em_plan *plan, double *est, int32_t *iters, int32_t *status,
                            int64_t *nnz_nonzero);
-/* what the pack kernels kept per group: live columns (Y != 0) and the entries with
- * aval != 0 inside them -- the part of the group the EM loop actually iterates on */
-int bambu_em_plan_download_live(bambu_em_plan *plan, int32_t *live_cols, int32_t *live_nnz);
+/* what the pack kernels kept per group: live columns (Y != 0), the entries with
+ * aval != 0 inside them -- the part of the group the EM loop actually iterates on --
+ * the shared memory its EM needs and the number of 32-lane slots of its image.
+ * Any pointer may be NULL. */
+int bambu_em_plan_download_live(bambu_em_plan *plan, int32_t *live_cols, int32_t *live_nnz,
+                                int32_t *smem_bytes, int32_t *slots);
 int bambu_em_plan_sync(bambu_em_plan *plan);
 /* device pointers of the outputs (est: 3*total_rows f64; iters, status: n_groups i32) */
 int bambu_em_plan_device_outputs(bambu_em_plan *plan, double **d_est, int32_t **d_iters,
                                  int32_t **d_status);
 /* device time of the last completed run, from CUDA events on the launch stream:
- * pack kernels, EM kernels, whole run.  Waits for the run. */
+ * pack + SELL kernels (start -> all images built), EM kernels (-> end), whole run.
+ * Waits for the run. */
 int bambu_em_plan_last_run_ms(bambu_em_plan *plan, float *pack_ms, float *em_ms, float *total_ms);
 /* kernels launched by the last run */
 int bambu_em_plan_last_run_launches(bambu_em_plan *plan, int32_t *n_launches);

@@ -122,7 +122,7 @@ def test_stopping_rule_parameters(em, oracle_mod):
         if par.get("maxiter", 10000) <= 7:
             assert iters.max() <= max(par["maxiter"] - 1, 0)
     _, iters, status = check_against_oracle(em, oracle_mod, a, maxiter=3, conv=1e-12)
-    assert iters.max() == 2 and ((status & 1) == (iters == 2)).all()
+    assert iters.max() == 2 and (status[iters < 2] & 1 == 0).all() and (status & 1).any()
 
 
 def test_nan_poisoning_group(em, oracle_mod):

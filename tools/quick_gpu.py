@@ -21,7 +21,7 @@ with EmPlan(a) as plan:
         ms = plan.last_run_ms()
         print("run", rep, ms)
     est, iters, status, nz = plan.download(want_nnz=True)
-    nl, nzl = plan.download_live()
+    nl, nzl = plan.download_live(); sm, sl = plan.download_image_stats(); print("smem pct", np.percentile(sm,[0,10,50,90,99,100]), "slots*640 total MB", sl.sum()*640/1e6, "smem class hist", np.bincount(np.searchsorted([7168,14336,28672,57344,115712,232192], sm)))
     work = float((nz * iters).sum())
     live = float((nzl.astype(np.int64) * iters).sum())
     print("nnz-iters %.3f G (live %.3f G)  -> %.1f G nnz-it/s (live %.1f)  iters max %d  device MB %.0f launches %d" % (
