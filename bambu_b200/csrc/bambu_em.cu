@@ -1,13 +1,18 @@
 // bambu_em.cu -- host side of libbambu_em.so: the C ABI of include/bambu_em.h,
-// the size-bucket scheduler and the kernel launches.  No torch, no CPU fallback.
+// the size-class scheduler, the chunked H2D / compute / D2H pipeline and the kernel
+// launches.  No torch, no CPU fallback.
 //
 // Replaces the serial lapply over gene groups of abundance_quantification()
-// (R/bambu-quantify_utilityFunctions.R:379-391) by, per size bucket, one pack
-// launch + one persistent EM launch on its own stream.
+// (R/bambu-quantify_utilityFunctions.R:379-391).  A *slot* processes one contiguous
+// range of gene groups (a chunk): per pack class one pack + one SELL launch, then per
+// EM class one persistent EM launch, each on its own stream.  The plan API is one
+// slot over the whole arena; bambu_em_batched() streams the arena through three
+// cached slots so that copies and kernels of neighbouring chunks overlap.
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -45,6 +50,7 @@ static int fail(int code, const char *fmt, ...)
                         "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,     \
                         __LINE__);                                                            \
     } while (0)
+#define TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
 static int g_device = 0;
 static bool g_device_checked = false;
@@ -76,7 +82,7 @@ static int ensure_device()
 // ------------------------------------------------------------------------------
 // size classes
 // ------------------------------------------------------------------------------
-// Pack buckets: groups whose WORST-CASE footprint (all columns live, no zero entries;
+// Pack classes: groups whose WORST-CASE footprint (all columns live, no zero entries;
 // known on the host from the pointer arrays) falls in one class; the class fixes the
 // CTA size and scratch shared memory of the pack + SELL kernels.
 // EM classes: the sell kernel measures the ACTUAL shared memory a group's EM needs and
@@ -103,15 +109,8 @@ static const EmClass kEmClasses[kNumClasses] = {
     {113u * 1024u, 512},   // 2
     {kSmemMax, 1024},      // 1
 };
-
-struct Bucket {   // pack bucket
-    int threads = 0;
-    uint32_t smem_pack = 0, smem_sell = 0;
-    std::vector<int32_t> work;     // group ids, largest first
-    int32_t *d_work = nullptr;     // view into plan->d_work_all
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-};
+static int g_em_grid[kNumClasses] = {};
+static bool g_em_configured = false;
 
 struct Ctrl {   // device control block, zeroed at the start of every run
     int err;
@@ -121,54 +120,141 @@ struct Ctrl {   // device control block, zeroed at the start of every run
     int ticket[8];
 };
 
-struct bambu_em_plan {
-    int64_t n_groups = 0, total_rows = 0, total_cols = 0, nnz = 0;
-    // device: structure
-    int64_t *d_grp_row_ptr = nullptr, *d_grp_col_ptr = nullptr, *d_row_nnz_ptr = nullptr;
-    // device: payload (owned unless bound)
-    bool payload_owned = false, payload_ready = false;
-    void *d_payload = nullptr;
-    const int32_t *d_col_idx = nullptr;
-    const double *d_aval = nullptr;
-    const uint8_t *d_nz_flags = nullptr;
-    const double *d_Y = nullptr, *d_K = nullptr;
-    const uint8_t *d_col_flags = nullptr;
-    // device: images + outputs
-    uint8_t *d_img = nullptr;        // stage-1 images (compact CSR + CSC), worst-case offsets
-    int64_t img_bytes = 0;
-    int64_t *d_img_off = nullptr;
-    PackInfo *d_info = nullptr;
-    uint8_t *d_pool = nullptr;       // SELL images, bump-allocated by the sell kernel
+// ------------------------------------------------------------------------------
+// grow-only buffers
+// ------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes, int64_t *account)
+    {
+        bytes = std::max<size_t>(bytes, 256);
+        if (bytes <= cap) return BAMBU_EM_OK;
+        if (p) { cudaFree(p); if (account) *account -= (int64_t)cap; }
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8;          // head-room: chunks differ a little in size
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&p, want); }
+        if (e != cudaSuccess) return fail(BAMBU_EM_ENOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        cap = want;
+        if (account) *account += (int64_t)cap;
+        return BAMBU_EM_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename Tp> Tp *as() const { return reinterpret_cast<Tp *>(p); }
+};
+
+struct PinBuf {   // pinned host staging
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        bytes = std::max<size_t>(bytes, 256);
+        if (bytes <= cap) return BAMBU_EM_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) return fail(BAMBU_EM_ENOMEM, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+        cap = want;
+        return BAMBU_EM_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename Tp> Tp *as() const { return reinterpret_cast<Tp *>(p); }
+};
+
+// ------------------------------------------------------------------------------
+// slot: everything needed to take one range of gene groups through the kernels
+// ------------------------------------------------------------------------------
+struct Bucket {   // pack bucket of the current chunk
+    int n = 0;                 // groups
+    int32_t *d_work = nullptr; // view into the slot's work buffer
+    uint32_t smem_pack = 0, smem_sell = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+};
+
+struct Slot {
+    // the range
+    int64_t g0 = 0, g1 = 0, r0 = 0, r1 = 0, c0 = 0, c1 = 0, e0 = 0, e1 = 0;
+    int64_t ng() const { return g1 - g0; }
+    int64_t rows() const { return r1 - r0; }
+    int64_t cols() const { return c1 - c0; }
+    int64_t nnz() const { return e1 - e0; }
+    bool single_tx_shortcut = true;   // R/bambu-quantify_utilityFunctions.R:410-414 (run_parallel, not emWithL1)
+    // device buffers (grow-only)
+    DevBuf grp_row_ptr, grp_col_ptr, row_nnz_ptr, payload, img, img_off, info, pool, ginfo, queue, nnz_nonzero, est,
+        iters, status, work, ctrl;
     int64_t pool_bytes = 0;
-    GroupImg *d_ginfo = nullptr;
-    int32_t *d_queue = nullptr;      // kNumClasses x n_groups
-    int64_t *d_nnz_nonzero = nullptr;
-    double *d_est = nullptr;
-    int32_t *d_iters = nullptr, *d_status = nullptr;
-    int32_t *d_work_all = nullptr;
-    Ctrl *d_ctrl = nullptr;
-    std::vector<Bucket> buckets;
-    std::vector<int32_t> single_tx;   // M == 1 groups: closed form in the pack kernel only
+    // payload views (device, already shifted so that absolute arena indices work)
+    bool payload_bound = false, payload_ready = false;
+    const int32_t *v_col_idx = nullptr;
+    const double *v_aval = nullptr;
+    const uint8_t *v_nz_flags = nullptr;
+    const double *v_Y = nullptr, *v_K = nullptr;
+    const uint8_t *v_col_flags = nullptr;
+    // host staging (pinned): img_off + work lists of the current chunk
+    PinBuf h_img_off, h_work;
+    Bucket buckets[8];
+    int n_single = 0;
+    int32_t *d_single = nullptr;
+    // streams / events
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t em_stream[kNumClasses] = {};
     cudaEvent_t em_done[kNumClasses] = {};
-    int em_grid[kNumClasses] = {};
-    cudaEvent_t ev_start = nullptr, ev_fork = nullptr, ev_packed = nullptr, ev_end = nullptr;
-    bool ran = false, finished = false;
-    bool single_tx_shortcut = true;   // R/bambu-quantify_utilityFunctions.R:410-414 (run_parallel, not emWithL1)
-    int32_t last_maxiter = 0;
-    double last_minvalue = 0, last_conv = 0;
-    int last_launches = 0;
+    cudaEvent_t ev_start = nullptr, ev_fork = nullptr, ev_packed = nullptr, ev_end = nullptr, ev_free = nullptr;
+    bool inited = false, prepared = false, ran = false, finished = false, busy = false;
+    EmParams P = {};
+    int launches = 0;
     int64_t device_bytes = 0;
+    // pending download of a pipelined chunk (batched path)
+    double *dl_est = nullptr;
+    int32_t *dl_iters = nullptr, *dl_status = nullptr;
+    int64_t dl_total_rows = 0;
 };
 
-template <typename Tp>
-static int dev_alloc(bambu_em_plan *p, Tp **ptr, size_t count)
+static int slot_init(Slot &s)
 {
-    size_t bytes = std::max<size_t>(count * sizeof(Tp), 16);
-    CUDA_TRY(cudaMalloc((void **)ptr, bytes));
-    p->device_bytes += (int64_t)bytes;
+    if (s.inited) return BAMBU_EM_OK;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s.own_stream, cudaStreamNonBlocking));
+    s.stream = s.own_stream;
+    CUDA_TRY(cudaEventCreate(&s.ev_start));
+    CUDA_TRY(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreate(&s.ev_packed));
+    CUDA_TRY(cudaEventCreate(&s.ev_end));
+    CUDA_TRY(cudaEventCreateWithFlags(&s.ev_free, cudaEventDisableTiming));
+    for (int c = 0; c < kNumClasses; ++c) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&s.em_stream[c], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&s.em_done[c], cudaEventDisableTiming));
+    }
+    for (int b = 0; b < kNumPackClasses; ++b) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&s.buckets[b].stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&s.buckets[b].done, cudaEventDisableTiming));
+    }
+    s.inited = true;
     return BAMBU_EM_OK;
+}
+
+static void slot_destroy(Slot &s)
+{
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    for (int b = 0; b < kNumPackClasses; ++b) {
+        if (s.buckets[b].stream) { cudaStreamSynchronize(s.buckets[b].stream); cudaStreamDestroy(s.buckets[b].stream); }
+        if (s.buckets[b].done) cudaEventDestroy(s.buckets[b].done);
+    }
+    for (int c = 0; c < kNumClasses; ++c) {
+        if (s.em_stream[c]) { cudaStreamSynchronize(s.em_stream[c]); cudaStreamDestroy(s.em_stream[c]); }
+        if (s.em_done[c]) cudaEventDestroy(s.em_done[c]);
+    }
+    for (cudaEvent_t e : {s.ev_start, s.ev_fork, s.ev_packed, s.ev_end, s.ev_free})
+        if (e) cudaEventDestroy(e);
+    if (s.own_stream) cudaStreamDestroy(s.own_stream);
+    for (DevBuf *b : {&s.grp_row_ptr, &s.grp_col_ptr, &s.row_nnz_ptr, &s.payload, &s.img, &s.img_off, &s.info, &s.pool,
+                      &s.ginfo, &s.queue, &s.nnz_nonzero, &s.est, &s.iters, &s.status, &s.work, &s.ctrl})
+        b->release();
+    s.h_img_off.release();
+    s.h_work.release();
+    s = Slot();
 }
 
 // ------------------------------------------------------------------------------
@@ -182,41 +268,7 @@ static ClassBounds class_bounds()
 }
 
 template <int T>
-static int launch_pack_T(bambu_em_plan *p, Bucket &b, const ArenaDev &A)
-{
-    auto pack = pack_resident_kernel<T>;
-    auto sell = sell_kernel<T>;
-    CUDA_TRY(cudaFuncSetAttribute(pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.smem_pack));
-    CUDA_TRY(cudaFuncSetAttribute(sell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.smem_sell));
-    const int n_work = (int)b.work.size();
-    CUDA_TRY(cudaEventRecord(b.ev0, b.stream));
-    pack<<<n_work, T, b.smem_pack, b.stream>>>(A, b.d_work, n_work, p->d_img_off, p->d_img, p->d_info,
-                                                p->d_nnz_nonzero, p->d_est, p->d_status, &p->d_ctrl->err,
-                                                p->single_tx_shortcut ? 1 : 0);
-    CUDA_TRY(cudaGetLastError());
-    sell<<<n_work, T, b.smem_sell, b.stream>>>(b.d_work, n_work, p->d_grp_row_ptr, p->d_img_off, p->d_img, p->d_info,
-                                                p->d_pool, (unsigned long long)p->pool_bytes, &p->d_ctrl->pool_ctr,
-                                                p->d_ginfo, class_bounds(), p->d_queue, p->n_groups,
-                                                p->d_ctrl->qcount, &p->d_ctrl->err);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(b.ev1, b.stream));
-    p->last_launches += 2;
-    return BAMBU_EM_OK;
-}
-
-static int launch_pack(bambu_em_plan *p, Bucket &b, const ArenaDev &A)
-{
-    switch (b.threads) {
-    case 64: return launch_pack_T<64>(p, b, A);
-    case 128: return launch_pack_T<128>(p, b, A);
-    case 256: return launch_pack_T<256>(p, b, A);
-    case 512: return launch_pack_T<512>(p, b, A);
-    }
-    return fail(BAMBU_EM_EINVAL, "no pack kernel instance for %d threads", b.threads);
-}
-
-template <int T>
-static int em_config_T(int c, int *grid)
+static int em_config_T(int c)
 {
     auto em = em_sell_kernel<T>;
     const uint32_t smem = kEmClasses[c].max_bytes;
@@ -224,51 +276,369 @@ static int em_config_T(int c, int *grid)
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em, T, smem));
     if (per_sm < 1) return fail(BAMBU_EM_ECUDA, "EM kernel class %d does not fit an SM", c);
-    *grid = per_sm * g_num_sms;
+    g_em_grid[c] = per_sm * g_num_sms;
     return BAMBU_EM_OK;
 }
 
 template <int T>
-static int launch_em_T(bambu_em_plan *p, int c, const EmParams &P)
+static int pack_config_T()
 {
-    em_sell_kernel<T><<<p->em_grid[c], T, kEmClasses[c].max_bytes, p->em_stream[c]>>>(
-        p->d_queue + (int64_t)c * p->n_groups, p->d_ctrl->qcount + c, p->d_ctrl->ticket + c, p->d_ginfo, p->d_pool,
-        p->d_grp_row_ptr, p->total_rows, P, p->d_est, p->d_iters, p->d_status);
-    CUDA_TRY(cudaGetLastError());
-    p->last_launches += 1;
+    CUDA_TRY(cudaFuncSetAttribute(pack_resident_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    CUDA_TRY(cudaFuncSetAttribute(sell_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     return BAMBU_EM_OK;
 }
 
-static int em_config(int c, int *grid)
+static int configure_kernels()
+{
+    if (g_em_configured) return BAMBU_EM_OK;
+    for (int c = 0; c < kNumClasses; ++c) {
+        switch (kEmClasses[c].threads) {
+        case 64: TRY(em_config_T<64>(c)); break;
+        case 128: TRY(em_config_T<128>(c)); break;
+        case 256: TRY(em_config_T<256>(c)); break;
+        case 512: TRY(em_config_T<512>(c)); break;
+        case 1024: TRY(em_config_T<1024>(c)); break;
+        default: return fail(BAMBU_EM_EINVAL, "no EM kernel instance for %d threads", kEmClasses[c].threads);
+        }
+    }
+    TRY(pack_config_T<64>());
+    TRY(pack_config_T<128>());
+    TRY(pack_config_T<256>());
+    TRY(pack_config_T<512>());
+    g_em_configured = true;
+    return BAMBU_EM_OK;
+}
+
+struct SlotViews {   // device pointers shifted so that absolute group / row / column / entry indices work
+    ArenaDev A;
+    const int64_t *img_off;
+    PackInfo *info;
+    GroupImg *ginfo;
+    int64_t *nnz_nonzero;
+    double *est;
+    int32_t *iters, *status;
+    Ctrl *ctrl;
+};
+
+static SlotViews slot_views(const Slot &s)
+{
+    SlotViews v;
+    v.A.grp_row_ptr = s.grp_row_ptr.as<int64_t>() - s.g0;
+    v.A.grp_col_ptr = s.grp_col_ptr.as<int64_t>() - s.g0;
+    v.A.row_nnz_ptr = s.row_nnz_ptr.as<int64_t>() - s.r0;
+    v.A.col_idx = s.v_col_idx; v.A.aval = s.v_aval; v.A.nz_flags = s.v_nz_flags;
+    v.A.Y = s.v_Y; v.A.K = s.v_K; v.A.col_flags = s.v_col_flags;
+    v.A.n_groups = s.ng();
+    v.A.total_rows = s.rows();
+    v.img_off = s.img_off.as<int64_t>() - s.g0;
+    v.info = s.info.as<PackInfo>() - s.g0;
+    v.ginfo = s.ginfo.as<GroupImg>() - s.g0;
+    v.nnz_nonzero = s.nnz_nonzero.as<int64_t>() - s.g0;
+    v.est = s.est.as<double>() - s.r0;     // est[k*rows + (row - r0)]
+    v.iters = s.iters.as<int32_t>() - s.g0;
+    v.status = s.status.as<int32_t>() - s.g0;
+    v.ctrl = s.ctrl.as<Ctrl>();
+    return v;
+}
+
+template <int T>
+static int launch_pack_T(Slot &s, Bucket &b, const SlotViews &v)
+{
+    pack_resident_kernel<T><<<b.n, T, b.smem_pack, b.stream>>>(v.A, b.d_work, b.n, v.img_off, s.img.as<uint8_t>(), v.info,
+                                                                v.nnz_nonzero, v.est, v.status, &v.ctrl->err,
+                                                                s.single_tx_shortcut ? 1 : 0);
+    CUDA_TRY(cudaGetLastError());
+    sell_kernel<T><<<b.n, T, b.smem_sell, b.stream>>>(b.d_work, b.n, v.A.grp_row_ptr, v.img_off, s.img.as<uint8_t>(), v.info,
+                                                       s.pool.as<uint8_t>(), (unsigned long long)s.pool_bytes,
+                                                       &v.ctrl->pool_ctr, v.ginfo, class_bounds(), s.queue.as<int32_t>(),
+                                                       std::max<int64_t>(s.ng(), 1), v.ctrl->qcount, &v.ctrl->err);
+    CUDA_TRY(cudaGetLastError());
+    s.launches += 2;
+    return BAMBU_EM_OK;
+}
+
+template <int T>
+static int launch_em_T(Slot &s, int c, const SlotViews &v)
+{
+    em_sell_kernel<T><<<g_em_grid[c], T, kEmClasses[c].max_bytes, s.em_stream[c]>>>(
+        s.queue.as<int32_t>() + (int64_t)c * std::max<int64_t>(s.ng(), 1), v.ctrl->qcount + c, v.ctrl->ticket + c, v.ginfo,
+        s.pool.as<uint8_t>(), v.A.grp_row_ptr, s.rows(), s.P, v.est, v.iters, v.status);
+    CUDA_TRY(cudaGetLastError());
+    s.launches += 1;
+    return BAMBU_EM_OK;
+}
+
+static int launch_pack(Slot &s, int bi, const SlotViews &v)
+{
+    Bucket &b = s.buckets[bi];
+    switch (kPackClasses[bi].threads) {
+    case 64: return launch_pack_T<64>(s, b, v);
+    case 128: return launch_pack_T<128>(s, b, v);
+    case 256: return launch_pack_T<256>(s, b, v);
+    case 512: return launch_pack_T<512>(s, b, v);
+    }
+    return fail(BAMBU_EM_EINVAL, "no pack kernel instance for %d threads", kPackClasses[bi].threads);
+}
+
+static int launch_em(Slot &s, int c, const SlotViews &v)
 {
     switch (kEmClasses[c].threads) {
-    case 64: return em_config_T<64>(c, grid);
-    case 128: return em_config_T<128>(c, grid);
-    case 256: return em_config_T<256>(c, grid);
-    case 512: return em_config_T<512>(c, grid);
-    case 1024: return em_config_T<1024>(c, grid);
+    case 64: return launch_em_T<64>(s, c, v);
+    case 128: return launch_em_T<128>(s, c, v);
+    case 256: return launch_em_T<256>(s, c, v);
+    case 512: return launch_em_T<512>(s, c, v);
+    case 1024: return launch_em_T<1024>(s, c, v);
     }
     return fail(BAMBU_EM_EINVAL, "no EM kernel instance for %d threads", kEmClasses[c].threads);
 }
 
-static int launch_em(bambu_em_plan *p, int c, const EmParams &P)
+// ------------------------------------------------------------------------------
+// slot_prepare: host-side analysis of the range [g0, g1) + upload of its structure
+// ------------------------------------------------------------------------------
+// grp_row_ptr / grp_col_ptr / row_nnz_ptr are the caller's HOST arrays of the whole arena.
+static int slot_prepare(Slot &s, const int64_t *grp_row_ptr, const int64_t *grp_col_ptr, const int64_t *row_nnz_ptr,
+                        int64_t g0, int64_t g1)
 {
-    switch (kEmClasses[c].threads) {
-    case 64: return launch_em_T<64>(p, c, P);
-    case 128: return launch_em_T<128>(p, c, P);
-    case 256: return launch_em_T<256>(p, c, P);
-    case 512: return launch_em_T<512>(p, c, P);
-    case 1024: return launch_em_T<1024>(p, c, P);
+    TRY(slot_init(s));
+    TRY(configure_kernels());
+    s.g0 = g0; s.g1 = g1;
+    s.r0 = grp_row_ptr[g0]; s.r1 = grp_row_ptr[g1];
+    s.c0 = grp_col_ptr[g0]; s.c1 = grp_col_ptr[g1];
+    s.e0 = row_nnz_ptr[s.r0]; s.e1 = row_nnz_ptr[s.r1];
+    const int64_t ng = s.ng();
+    if (ng > INT32_MAX / kNumClasses) return fail(BAMBU_EM_EINVAL, "too many groups in one chunk");
+    for (int64_t r = s.r0; r < s.r1; ++r)
+        if (row_nnz_ptr[r + 1] < row_nnz_ptr[r]) return fail(BAMBU_EM_EINVAL, "row_nnz_ptr decreases at row %lld", (long long)r);
+
+    // ---- classify by worst-case footprint, lay out the stage-1 images ---------------
+    TRY(s.h_img_off.ensure(sizeof(int64_t) * (size_t)(ng + 1)));
+    TRY(s.h_work.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(ng, 1)));
+    int64_t *img_off = s.h_img_off.as<int64_t>();
+    std::vector<int32_t> per_class[8];
+    std::vector<int32_t> single;
+    std::vector<int64_t> gnnz((size_t)ng, 0);
+    uint32_t smem_pack[8] = {}, smem_sell[8] = {};
+    int64_t off = 0;
+    for (int64_t g = g0; g < g1; ++g) {
+        const int64_t M = grp_row_ptr[g + 1] - grp_row_ptr[g], N = grp_col_ptr[g + 1] - grp_col_ptr[g];
+        if (M < 0 || N < 0) return fail(BAMBU_EM_EINVAL, "group %lld has negative extent", (long long)g);
+        const int64_t e = row_nnz_ptr[grp_row_ptr[g + 1]] - row_nnz_ptr[grp_row_ptr[g]];
+        gnnz[g - g0] = e;
+        img_off[g - g0] = off;
+        if (M == 0) continue;
+        if (M == 1 && s.single_tx_shortcut) { single.push_back((int32_t)g); continue; }
+        const double ub = 20.0 * (double)e + 18.0 * (double)(M + N) + 64.0;
+        if (M > kMaxIndex || N > kMaxIndex || ub > (double)kSmemMax)
+            return fail(BAMBU_EM_EINVAL,
+                        "group %lld (M=%lld N=%lld entries=%lld) exceeds the shared-memory resident tier",
+                        (long long)g, (long long)M, (long long)N, (long long)e);
+        const uint32_t bytes = em_smem_bytes((uint32_t)M, (uint32_t)N, (uint32_t)e);
+        int c = 0;
+        while (c < kNumPackClasses - 1 && bytes > kPackClasses[c].max_bytes) ++c;
+        per_class[c].push_back((int32_t)g);
+        smem_pack[c] = std::max(smem_pack[c], pack_smem_bytes((uint32_t)M, (uint32_t)N));
+        smem_sell[c] = std::max(smem_sell[c], sell_scratch_bytes((uint32_t)M, (uint32_t)N));
+        off += img_layout((uint32_t)M, (uint32_t)N, (uint32_t)e).total;
     }
-    return fail(BAMBU_EM_EINVAL, "no EM kernel instance for %d threads", kEmClasses[c].threads);
+    img_off[ng] = off;
+
+    // work lists: per pack class, largest groups first (they are queued for the EM first)
+    int32_t *work = s.h_work.as<int32_t>();
+    size_t woff = 0;
+    TRY(s.work.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(ng, 1), &s.device_bytes));
+    for (int c = 0; c < kNumPackClasses; ++c) {
+        auto &w = per_class[c];
+        std::stable_sort(w.begin(), w.end(), [&](int32_t x, int32_t y) { return gnnz[x - g0] > gnnz[y - g0]; });
+        std::copy(w.begin(), w.end(), work + woff);
+        s.buckets[c].n = (int)w.size();
+        s.buckets[c].d_work = s.work.as<int32_t>() + woff;
+        s.buckets[c].smem_pack = smem_pack[c];
+        s.buckets[c].smem_sell = smem_sell[c];
+        woff += w.size();
+    }
+    std::copy(single.begin(), single.end(), work + woff);
+    s.n_single = (int)single.size();
+    s.d_single = s.work.as<int32_t>() + woff;
+    woff += single.size();
+
+    // ---- device buffers ------------------------------------------------------------------
+    const int64_t rows = s.rows(), nnz = s.nnz(), cols = s.cols();
+    // SELL pool: typical need is ~25 B per live entry + ~40 B per row / live column; grown on demand
+    int64_t pool = (int64_t)(24.0 * (double)nnz + 48.0 * (double)(rows + cols)) + (4 << 20);
+    pool = (pool + 15) / 16 * 16;
+    s.pool_bytes = std::max<int64_t>(pool, (int64_t)s.pool.cap / 16 * 16);
+    TRY(s.grp_row_ptr.ensure(8 * (size_t)(ng + 1), &s.device_bytes));
+    TRY(s.grp_col_ptr.ensure(8 * (size_t)(ng + 1), &s.device_bytes));
+    TRY(s.row_nnz_ptr.ensure(8 * (size_t)(rows + 1), &s.device_bytes));
+    TRY(s.img.ensure((size_t)off, &s.device_bytes));
+    TRY(s.pool.ensure((size_t)s.pool_bytes, &s.device_bytes));
+    TRY(s.img_off.ensure(8 * (size_t)(ng + 1), &s.device_bytes));
+    TRY(s.info.ensure(sizeof(PackInfo) * (size_t)ng, &s.device_bytes));
+    TRY(s.ginfo.ensure(sizeof(GroupImg) * (size_t)ng, &s.device_bytes));
+    TRY(s.queue.ensure(4 * (size_t)kNumClasses * (size_t)std::max<int64_t>(ng, 1), &s.device_bytes));
+    TRY(s.nnz_nonzero.ensure(8 * (size_t)ng, &s.device_bytes));
+    TRY(s.est.ensure(8 * 3 * (size_t)rows, &s.device_bytes));
+    TRY(s.iters.ensure(4 * (size_t)ng, &s.device_bytes));
+    TRY(s.status.ensure(4 * (size_t)ng, &s.device_bytes));
+    TRY(s.ctrl.ensure(sizeof(Ctrl), &s.device_bytes));
+
+    cudaStream_t st = s.stream;
+    CUDA_TRY(cudaMemcpyAsync(s.grp_row_ptr.p, grp_row_ptr + g0, 8 * (size_t)(ng + 1), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s.grp_col_ptr.p, grp_col_ptr + g0, 8 * (size_t)(ng + 1), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s.row_nnz_ptr.p, row_nnz_ptr + s.r0, 8 * (size_t)(rows + 1), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s.img_off.p, img_off, 8 * (size_t)(ng + 1), cudaMemcpyHostToDevice, st));
+    if (woff) CUDA_TRY(cudaMemcpyAsync(s.work.p, work, 4 * woff, cudaMemcpyHostToDevice, st));
+    s.prepared = true;
+    s.ran = s.finished = false;
+    return BAMBU_EM_OK;
+}
+
+// H2D of the range's payload from the caller's HOST arrays of the whole arena
+static int slot_upload(Slot &s, const int32_t *col_idx, const double *aval, const uint8_t *nz_flags, const double *Y,
+                       const double *K, const uint8_t *col_flags)
+{
+    const size_t nnz = (size_t)s.nnz(), nc = (size_t)s.cols();
+    if ((nnz && (!col_idx || !aval || !nz_flags)) || (nc && (!Y || !K || !col_flags)))
+        return fail(BAMBU_EM_EINVAL, "NULL payload pointer");
+    // one allocation: aval | Y | K | col_idx | nz_flags | col_flags  (8-byte items first)
+    TRY(s.payload.ensure(8 * nnz + 16 * nc + 4 * nnz + nnz + nc + 64, &s.device_bytes));
+    uint8_t *q = s.payload.as<uint8_t>();
+    double *d_aval = (double *)q; q += 8 * nnz;
+    double *d_Y = (double *)q; q += 8 * nc;
+    double *d_K = (double *)q; q += 8 * nc;
+    int32_t *d_ci = (int32_t *)q; q += 4 * nnz;
+    uint8_t *d_nf = q; q += nnz;
+    uint8_t *d_cf = q;
+    cudaStream_t st = s.stream;
+    if (nnz) {
+        CUDA_TRY(cudaMemcpyAsync(d_aval, aval + s.e0, 8 * nnz, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_ci, col_idx + s.e0, 4 * nnz, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_nf, nz_flags + s.e0, nnz, cudaMemcpyHostToDevice, st));
+    }
+    if (nc) {
+        CUDA_TRY(cudaMemcpyAsync(d_Y, Y + s.c0, 8 * nc, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_K, K + s.c0, 8 * nc, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_cf, col_flags + s.c0, nc, cudaMemcpyHostToDevice, st));
+    }
+    s.v_aval = d_aval - s.e0; s.v_col_idx = d_ci - s.e0; s.v_nz_flags = d_nf - s.e0;
+    s.v_Y = d_Y - s.c0; s.v_K = d_K - s.c0; s.v_col_flags = d_cf - s.c0;
+    s.payload_bound = false;
+    s.payload_ready = true;
+    return BAMBU_EM_OK;
+}
+
+static int slot_enqueue(Slot &s)
+{
+    const SlotViews v = slot_views(s);
+    cudaStream_t st = s.stream;
+    const size_t ng = (size_t)std::max<int64_t>(s.ng(), 1);
+    s.launches = 0;
+    CUDA_TRY(cudaEventRecord(s.ev_start, st));
+    CUDA_TRY(cudaMemsetAsync(s.ctrl.p, 0, sizeof(Ctrl), st));
+    CUDA_TRY(cudaMemsetAsync(s.iters.p, 0, 4 * ng, st));
+    CUDA_TRY(cudaMemsetAsync(s.status.p, 0, 4 * ng, st));
+    CUDA_TRY(cudaMemsetAsync(s.est.p, 0, 8 * (size_t)std::max<int64_t>(3 * s.rows(), 1), st));
+    CUDA_TRY(cudaMemsetAsync(s.info.p, 0, sizeof(PackInfo) * ng, st));
+    CUDA_TRY(cudaMemsetAsync(s.ginfo.p, 0, sizeof(GroupImg) * ng, st));
+    CUDA_TRY(cudaMemsetAsync(s.nnz_nonzero.p, 0, 8 * ng, st));
+    CUDA_TRY(cudaEventRecord(s.ev_fork, st));
+    bool any = false;
+    for (int b = 0; b < kNumPackClasses; ++b) {
+        if (!s.buckets[b].n) continue;
+        any = true;
+        CUDA_TRY(cudaStreamWaitEvent(s.buckets[b].stream, s.ev_fork, 0));
+        TRY(launch_pack(s, b, v));
+        CUDA_TRY(cudaEventRecord(s.buckets[b].done, s.buckets[b].stream));
+        CUDA_TRY(cudaStreamWaitEvent(st, s.buckets[b].done, 0));
+    }
+    if (s.n_single) {
+        pack_resident_kernel<64><<<s.n_single, 64, 0, st>>>(v.A, s.d_single, s.n_single, v.img_off, s.img.as<uint8_t>(),
+                                                            v.info, v.nnz_nonzero, v.est, v.status, &v.ctrl->err, 1);
+        CUDA_TRY(cudaGetLastError());
+        s.launches += 1;
+    }
+    CUDA_TRY(cudaEventRecord(s.ev_packed, st));
+    if (any) {   // EM, one class per stream; the queues were filled on the device
+        for (int c = kNumClasses - 1; c >= 0; --c) {
+            CUDA_TRY(cudaStreamWaitEvent(s.em_stream[c], s.ev_packed, 0));
+            TRY(launch_em(s, c, v));
+            CUDA_TRY(cudaEventRecord(s.em_done[c], s.em_stream[c]));
+            CUDA_TRY(cudaStreamWaitEvent(st, s.em_done[c], 0));
+        }
+    }
+    CUDA_TRY(cudaEventRecord(s.ev_end, st));
+    s.ran = true;
+    s.finished = false;
+    return BAMBU_EM_OK;
+}
+
+static int slot_run(Slot &s, int32_t maxiter, double minvalue, double conv)
+{
+    if (!s.prepared) return fail(BAMBU_EM_ESTATE, "run before the plan was prepared");
+    if (!s.payload_ready) return fail(BAMBU_EM_ESTATE, "run before upload/bind_device");
+    if (conv != conv || minvalue != minvalue) return fail(BAMBU_EM_EINVAL, "conv/minvalue is NaN");
+    s.P.maxiter = maxiter;
+    s.P.minvalue = minvalue;
+    s.P.conv = conv;
+    if (conv > 1e-290 && std::isfinite(conv)) {
+        s.P.conv_hi = conv * (1.0 + std::ldexp(1.0, -40));
+        s.P.conv_lo = conv * (1.0 - std::ldexp(1.0, -40));
+    } else {   // no screen: always take the exact division
+        s.P.conv_hi = INFINITY;
+        s.P.conv_lo = 0.0;
+    }
+    return slot_enqueue(s);
+}
+
+// wait for the run; if the SELL pool was too small, grow it and run again
+static int slot_finish(Slot &s)
+{
+    if (!s.ran || s.finished) return BAMBU_EM_OK;
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        int err = 0;
+        CUDA_TRY(cudaMemcpyAsync(&err, &s.ctrl.as<Ctrl>()->err, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(cudaStreamSynchronize(s.stream));
+        if (err == 0) { s.finished = true; return BAMBU_EM_OK; }
+        if (err == kErrColRange) return fail(BAMBU_EM_EINVAL, "col_idx outside its group's column range");
+        if (err == kErrColOrder) return fail(BAMBU_EM_EINVAL, "col_idx not strictly increasing inside a row");
+        if (err == kErrTooBig) return fail(BAMBU_EM_EINVAL, "a gene group's image exceeds the shared-memory resident tier");
+        if (err != kErrPool) return fail(BAMBU_EM_ECUDA, "device error word %d", err);
+        s.pool_bytes *= 2;
+        TRY(s.pool.ensure((size_t)s.pool_bytes, &s.device_bytes));
+        TRY(slot_enqueue(s));
+    }
+    return fail(BAMBU_EM_ENOMEM, "SELL image pool kept overflowing");
+}
+
+// D2H of the range's outputs into the caller's HOST arrays of the whole arena (asynchronous)
+static int slot_download_async(Slot &s, double *est, int64_t total_rows, int32_t *iters, int32_t *status, int64_t *nnz)
+{
+    cudaStream_t st = s.stream;
+    const size_t rows = (size_t)s.rows(), ng = (size_t)s.ng();
+    if (est && rows)
+        for (int k = 0; k < 3; ++k)
+            CUDA_TRY(cudaMemcpyAsync(est + (size_t)k * total_rows + s.r0, s.est.as<double>() + (size_t)k * rows, 8 * rows,
+                                     cudaMemcpyDeviceToHost, st));
+    if (iters && ng) CUDA_TRY(cudaMemcpyAsync(iters + s.g0, s.iters.p, 4 * ng, cudaMemcpyDeviceToHost, st));
+    if (status && ng) CUDA_TRY(cudaMemcpyAsync(status + s.g0, s.status.p, 4 * ng, cudaMemcpyDeviceToHost, st));
+    if (nnz && ng) CUDA_TRY(cudaMemcpyAsync(nnz + s.g0, s.nnz_nonzero.p, 8 * ng, cudaMemcpyDeviceToHost, st));
+    return BAMBU_EM_OK;
 }
 
 // ------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------
+struct bambu_em_plan {
+    Slot slot;
+    int64_t n_groups = 0;
+};
+
+static Slot g_pipe[3];            // cached slots of bambu_em_batched
+static bool g_pipe_used = false;
+
 extern "C" {
 
-const char *bambu_em_version(void) { return "bambu_em_b200 0.2.0 (sm_100a)"; }
+const char *bambu_em_version(void) { return "bambu_em_b200 0.3.0 (sm_100a)"; }
 const char *bambu_em_last_error(void) { return g_last_error.c_str(); }
 
 int bambu_em_device_count(void)
@@ -283,39 +653,43 @@ int bambu_em_device_count(void)
     return ok;
 }
 
+int bambu_em_shutdown(void)
+{
+    if (g_pipe_used) {
+        cudaSetDevice(g_device);
+        for (Slot &s : g_pipe) slot_destroy(s);
+        g_pipe_used = false;
+    }
+    return BAMBU_EM_OK;
+}
+
 int bambu_em_set_device(int device)
 {
     if (device < 0) return fail(BAMBU_EM_EINVAL, "negative device index");
+    if (device != g_device) {
+        bambu_em_shutdown();      // the cached workspace lives on the old device
+        g_em_configured = false;
+    }
     g_device = device;
     g_device_checked = false;
     return ensure_device();
+}
+
+static int check_arrays(int64_t n_groups, const int64_t *grp_row_ptr, const int64_t *grp_col_ptr,
+                        const int64_t *row_nnz_ptr)
+{
+    if (n_groups < 0 || n_groups > INT32_MAX) return fail(BAMBU_EM_EINVAL, "n_groups out of range");
+    if (!grp_row_ptr || !grp_col_ptr || !row_nnz_ptr) return fail(BAMBU_EM_EINVAL, "NULL pointer array");
+    if (grp_row_ptr[0] != 0 || grp_col_ptr[0] != 0 || row_nnz_ptr[0] != 0)
+        return fail(BAMBU_EM_EINVAL, "pointer arrays must start at 0");
+    return BAMBU_EM_OK;
 }
 
 int bambu_em_plan_destroy(bambu_em_plan *p)
 {
     if (!p) return BAMBU_EM_OK;
     cudaSetDevice(g_device);
-    if (p->stream) cudaStreamSynchronize(p->stream);
-    for (auto &b : p->buckets) {
-        if (b.stream) { cudaStreamSynchronize(b.stream); cudaStreamDestroy(b.stream); }
-        if (b.ev0) cudaEventDestroy(b.ev0);
-        if (b.ev1) cudaEventDestroy(b.ev1);
-    }
-    for (int c = 0; c < kNumClasses; ++c) {
-        if (p->em_stream[c]) { cudaStreamSynchronize(p->em_stream[c]); cudaStreamDestroy(p->em_stream[c]); }
-        if (p->em_done[c]) cudaEventDestroy(p->em_done[c]);
-    }
-    if (p->ev_start) cudaEventDestroy(p->ev_start);
-    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
-    if (p->ev_packed) cudaEventDestroy(p->ev_packed);
-    if (p->ev_end) cudaEventDestroy(p->ev_end);
-    if (p->own_stream) cudaStreamDestroy(p->own_stream);
-    cudaFree(p->d_grp_row_ptr); cudaFree(p->d_grp_col_ptr); cudaFree(p->d_row_nnz_ptr);
-    if (p->payload_owned) cudaFree(p->d_payload);
-    cudaFree(p->d_img); cudaFree(p->d_img_off); cudaFree(p->d_info); cudaFree(p->d_nnz_nonzero);
-    cudaFree(p->d_pool); cudaFree(p->d_ginfo); cudaFree(p->d_queue);
-    cudaFree(p->d_est); cudaFree(p->d_iters); cudaFree(p->d_status); cudaFree(p->d_work_all);
-    cudaFree(p->d_ctrl);
+    slot_destroy(p->slot);
     delete p;
     return BAMBU_EM_OK;
 }
@@ -325,124 +699,15 @@ static int plan_create_impl(bambu_em_plan **out, int64_t n_groups, const int64_t
 {
     if (!out) return fail(BAMBU_EM_EINVAL, "plan pointer is NULL");
     *out = nullptr;
-    if (n_groups < 0 || n_groups > INT32_MAX) return fail(BAMBU_EM_EINVAL, "n_groups out of range");
-    if (!grp_row_ptr || !grp_col_ptr || !row_nnz_ptr) return fail(BAMBU_EM_EINVAL, "NULL pointer array");
-    if (grp_row_ptr[0] != 0 || grp_col_ptr[0] != 0 || row_nnz_ptr[0] != 0)
-        return fail(BAMBU_EM_EINVAL, "pointer arrays must start at 0");
-    int rc = ensure_device();
-    if (rc) return rc;
-
+    TRY(check_arrays(n_groups, grp_row_ptr, grp_col_ptr, row_nnz_ptr));
+    TRY(ensure_device());
     bambu_em_plan *p = new (std::nothrow) bambu_em_plan;
     if (!p) return fail(BAMBU_EM_ENOMEM, "out of host memory");
     p->n_groups = n_groups;
-    p->single_tx_shortcut = single_tx_shortcut;
-    p->total_rows = grp_row_ptr[n_groups];
-    p->total_cols = grp_col_ptr[n_groups];
-    for (int64_t r = 0; r < p->total_rows; ++r)
-        if (row_nnz_ptr[r + 1] < row_nnz_ptr[r]) { delete p; return fail(BAMBU_EM_EINVAL, "row_nnz_ptr decreases at row %lld", (long long)r); }
-    p->nnz = row_nnz_ptr[p->total_rows];
-
-    // ---- classify groups by worst-case footprint, lay out the stage-1 images ------
-    std::vector<int64_t> img_off((size_t)n_groups + 1, 0);
-    std::vector<std::vector<int32_t>> per_class(kNumPackClasses);
-    std::vector<uint32_t> ub_pack((size_t)n_groups, 0), ub_sell((size_t)n_groups, 0);
-    std::vector<int64_t> gnnz((size_t)n_groups, 0);
-    int64_t off = 0;
-    for (int64_t g = 0; g < n_groups; ++g) {
-        const int64_t M = grp_row_ptr[g + 1] - grp_row_ptr[g], N = grp_col_ptr[g + 1] - grp_col_ptr[g];
-        if (M < 0 || N < 0) { delete p; return fail(BAMBU_EM_EINVAL, "group %lld has negative extent", (long long)g); }
-        const int64_t e = row_nnz_ptr[grp_row_ptr[g + 1]] - row_nnz_ptr[grp_row_ptr[g]];
-        gnnz[g] = e;
-        img_off[g] = off;
-        if (M == 0) continue;
-        if (M == 1 && single_tx_shortcut) { p->single_tx.push_back((int32_t)g); continue; }
-        const double ub = 20.0 * (double)e + 18.0 * (double)(M + N) + 64.0;
-        if (M > kMaxIndex || N > kMaxIndex || ub > (double)kSmemMax) {
-            delete p;
-            return fail(BAMBU_EM_EINVAL,
-                        "group %lld (M=%lld N=%lld entries=%lld) exceeds the shared-memory resident tier",
-                        (long long)g, (long long)M, (long long)N, (long long)e);
-        }
-        const uint32_t bytes = em_smem_bytes((uint32_t)M, (uint32_t)N, (uint32_t)e);
-        ub_pack[g] = pack_smem_bytes((uint32_t)M, (uint32_t)N);
-        ub_sell[g] = sell_scratch_bytes((uint32_t)M, (uint32_t)N);
-        int c = 0;
-        while (c < kNumPackClasses - 1 && bytes > kPackClasses[c].max_bytes) ++c;
-        per_class[c].push_back((int32_t)g);
-        off += img_layout((uint32_t)M, (uint32_t)N, (uint32_t)e).total;
-    }
-    img_off[n_groups] = off;
-    p->img_bytes = off;
-    // SELL pool: typical need is ~25 B per live entry + ~40 B per row/live column; grown on demand
-    p->pool_bytes = (int64_t)(24.0 * (double)p->nnz + 48.0 * (double)(p->total_rows + p->total_cols)) + (4 << 20);
-    p->pool_bytes = (p->pool_bytes + 15) / 16 * 16;
-
-    auto fail_destroy = [&](int code) { bambu_em_plan_destroy(p); return code; };
-#define PLAN_TRY(expr) do { int _rc = (expr); if (_rc) return fail_destroy(_rc); } while (0)
-#define PLAN_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { fail(_e == cudaErrorMemoryAllocation ? BAMBU_EM_ENOMEM : BAMBU_EM_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); return fail_destroy(_e == cudaErrorMemoryAllocation ? BAMBU_EM_ENOMEM : BAMBU_EM_ECUDA); } } while (0)
-
-    size_t n_work_total = p->single_tx.size();
-    for (int c = 0; c < kNumPackClasses; ++c) {
-        if (per_class[c].empty()) continue;
-        Bucket b;
-        b.threads = kPackClasses[c].threads;
-        b.work = std::move(per_class[c]);
-        std::stable_sort(b.work.begin(), b.work.end(), [&](int32_t x, int32_t y) { return gnnz[x] > gnnz[y]; });
-        for (int32_t g : b.work) {
-            b.smem_pack = std::max(b.smem_pack, ub_pack[g]);
-            b.smem_sell = std::max(b.smem_sell, ub_sell[g]);
-        }
-        n_work_total += b.work.size();
-        p->buckets.push_back(std::move(b));
-    }
-
-    PLAN_CUDA(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
-    p->stream = p->own_stream;
-    PLAN_CUDA(cudaEventCreate(&p->ev_start));
-    PLAN_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
-    PLAN_CUDA(cudaEventCreate(&p->ev_packed));
-    PLAN_CUDA(cudaEventCreate(&p->ev_end));
-    for (int c = 0; c < kNumClasses; ++c) {
-        PLAN_CUDA(cudaStreamCreateWithFlags(&p->em_stream[c], cudaStreamNonBlocking));
-        PLAN_CUDA(cudaEventCreateWithFlags(&p->em_done[c], cudaEventDisableTiming));
-        PLAN_TRY(em_config(c, &p->em_grid[c]));
-    }
-
-    PLAN_TRY(dev_alloc(p, &p->d_grp_row_ptr, (size_t)n_groups + 1));
-    PLAN_TRY(dev_alloc(p, &p->d_grp_col_ptr, (size_t)n_groups + 1));
-    PLAN_TRY(dev_alloc(p, &p->d_row_nnz_ptr, (size_t)p->total_rows + 1));
-    PLAN_TRY(dev_alloc(p, &p->d_img, (size_t)p->img_bytes));
-    PLAN_TRY(dev_alloc(p, &p->d_pool, (size_t)p->pool_bytes));
-    PLAN_TRY(dev_alloc(p, &p->d_img_off, (size_t)n_groups + 1));
-    PLAN_TRY(dev_alloc(p, &p->d_info, (size_t)n_groups));
-    PLAN_TRY(dev_alloc(p, &p->d_ginfo, (size_t)n_groups));
-    PLAN_TRY(dev_alloc(p, &p->d_queue, (size_t)kNumClasses * (size_t)std::max<int64_t>(n_groups, 1)));
-    PLAN_TRY(dev_alloc(p, &p->d_nnz_nonzero, (size_t)n_groups));
-    PLAN_TRY(dev_alloc(p, &p->d_est, (size_t)3 * p->total_rows));
-    PLAN_TRY(dev_alloc(p, &p->d_iters, (size_t)n_groups));
-    PLAN_TRY(dev_alloc(p, &p->d_status, (size_t)n_groups));
-    PLAN_TRY(dev_alloc(p, &p->d_work_all, n_work_total));
-    PLAN_TRY(dev_alloc(p, &p->d_ctrl, 1));
-
-    cudaStream_t s = p->stream;
-    PLAN_CUDA(cudaMemcpyAsync(p->d_grp_row_ptr, grp_row_ptr, sizeof(int64_t) * (n_groups + 1), cudaMemcpyHostToDevice, s));
-    PLAN_CUDA(cudaMemcpyAsync(p->d_grp_col_ptr, grp_col_ptr, sizeof(int64_t) * (n_groups + 1), cudaMemcpyHostToDevice, s));
-    PLAN_CUDA(cudaMemcpyAsync(p->d_row_nnz_ptr, row_nnz_ptr, sizeof(int64_t) * (p->total_rows + 1), cudaMemcpyHostToDevice, s));
-    PLAN_CUDA(cudaMemcpyAsync(p->d_img_off, img_off.data(), sizeof(int64_t) * (n_groups + 1), cudaMemcpyHostToDevice, s));
-    size_t woff = 0;
-    for (auto &b : p->buckets) {
-        b.d_work = p->d_work_all + woff;
-        PLAN_CUDA(cudaMemcpyAsync(b.d_work, b.work.data(), sizeof(int32_t) * b.work.size(), cudaMemcpyHostToDevice, s));
-        woff += b.work.size();
-        PLAN_CUDA(cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
-        PLAN_CUDA(cudaEventCreate(&b.ev0));
-        PLAN_CUDA(cudaEventCreate(&b.ev1));
-    }
-    if (!p->single_tx.empty())
-        PLAN_CUDA(cudaMemcpyAsync(p->d_work_all + woff, p->single_tx.data(), sizeof(int32_t) * p->single_tx.size(), cudaMemcpyHostToDevice, s));
-    PLAN_CUDA(cudaStreamSynchronize(s));   // the host vectors above go out of scope
-#undef PLAN_TRY
-#undef PLAN_CUDA
+    p->slot.single_tx_shortcut = single_tx_shortcut;
+    int rc = slot_prepare(p->slot, grp_row_ptr, grp_col_ptr, row_nnz_ptr, 0, n_groups);
+    if (!rc && cudaStreamSynchronize(p->slot.stream) != cudaSuccess) rc = fail(BAMBU_EM_ECUDA, "structure upload failed");
+    if (rc) { bambu_em_plan_destroy(p); return rc; }
     *out = p;
     return BAMBU_EM_OK;
 }
@@ -456,8 +721,8 @@ int bambu_em_plan_create(bambu_em_plan **out, int64_t n_groups, const int64_t *g
 int bambu_em_plan_set_stream(bambu_em_plan *p, void *cuda_stream)
 {
     if (!p) return fail(BAMBU_EM_EINVAL, "plan is NULL");
-    CUDA_TRY(cudaStreamSynchronize(p->stream));
-    p->stream = cuda_stream ? (cudaStream_t)cuda_stream : p->own_stream;
+    CUDA_TRY(cudaStreamSynchronize(p->slot.stream));
+    p->slot.stream = cuda_stream ? (cudaStream_t)cuda_stream : p->slot.own_stream;
     return BAMBU_EM_OK;
 }
 
@@ -465,34 +730,8 @@ int bambu_em_plan_upload(bambu_em_plan *p, const int32_t *col_idx, const double 
                          const double *Y, const double *K, const uint8_t *col_flags)
 {
     if (!p) return fail(BAMBU_EM_EINVAL, "plan is NULL");
-    if ((p->nnz && (!col_idx || !aval || !nz_flags)) || (p->total_cols && (!Y || !K || !col_flags)))
-        return fail(BAMBU_EM_EINVAL, "NULL payload pointer");
-    int rc = ensure_device();
-    if (rc) return rc;
-    if (!p->payload_owned) {
-        // one allocation: aval | Y | K | col_idx | nz_flags | col_flags  (8-byte items first)
-        const size_t nnz = (size_t)p->nnz, nc = (size_t)p->total_cols;
-        const size_t bytes = 8 * nnz + 16 * nc + 4 * nnz + nnz + nc + 64;
-        CUDA_TRY(cudaMalloc(&p->d_payload, bytes));
-        p->device_bytes += (int64_t)bytes;
-        uint8_t *q = (uint8_t *)p->d_payload;
-        p->d_aval = (double *)q; q += 8 * nnz;
-        p->d_Y = (double *)q; q += 8 * nc;
-        p->d_K = (double *)q; q += 8 * nc;
-        p->d_col_idx = (int32_t *)q; q += 4 * nnz;
-        p->d_nz_flags = q; q += nnz;
-        p->d_col_flags = q;
-        p->payload_owned = true;
-    }
-    cudaStream_t s = p->stream;
-    CUDA_TRY(cudaMemcpyAsync((void *)p->d_aval, aval, 8 * (size_t)p->nnz, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync((void *)p->d_col_idx, col_idx, 4 * (size_t)p->nnz, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync((void *)p->d_nz_flags, nz_flags, (size_t)p->nnz, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync((void *)p->d_Y, Y, 8 * (size_t)p->total_cols, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync((void *)p->d_K, K, 8 * (size_t)p->total_cols, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync((void *)p->d_col_flags, col_flags, (size_t)p->total_cols, cudaMemcpyHostToDevice, s));
-    p->payload_ready = true;
-    return BAMBU_EM_OK;
+    TRY(ensure_device());
+    return slot_upload(p->slot, col_idx, aval, nz_flags, Y, K, col_flags);
 }
 
 int bambu_em_plan_bind_device(bambu_em_plan *p, const int32_t *d_col_idx, const double *d_aval,
@@ -500,143 +739,38 @@ int bambu_em_plan_bind_device(bambu_em_plan *p, const int32_t *d_col_idx, const 
                               const uint8_t *d_col_flags)
 {
     if (!p) return fail(BAMBU_EM_EINVAL, "plan is NULL");
-    if (p->payload_owned) {
-        CUDA_TRY(cudaStreamSynchronize(p->stream));
-        cudaFree(p->d_payload);
-        p->d_payload = nullptr;
-        p->payload_owned = false;
-    }
-    p->d_col_idx = d_col_idx; p->d_aval = d_aval; p->d_nz_flags = d_nz_flags;
-    p->d_Y = d_Y; p->d_K = d_K; p->d_col_flags = d_col_flags;
-    p->payload_ready = true;
-    return BAMBU_EM_OK;
-}
-
-static int enqueue_run(bambu_em_plan *p)
-{
-    EmParams P;
-    const double conv = p->last_conv;
-    P.maxiter = p->last_maxiter;
-    P.minvalue = p->last_minvalue;
-    P.conv = conv;
-    if (conv > 1e-290 && std::isfinite(conv)) {
-        P.conv_hi = conv * (1.0 + std::ldexp(1.0, -40));
-        P.conv_lo = conv * (1.0 - std::ldexp(1.0, -40));
-    } else {   // no screen: always take the exact division
-        P.conv_hi = INFINITY;
-        P.conv_lo = 0.0;
-    }
-    ArenaDev A;
-    A.grp_row_ptr = p->d_grp_row_ptr; A.grp_col_ptr = p->d_grp_col_ptr; A.row_nnz_ptr = p->d_row_nnz_ptr;
-    A.col_idx = p->d_col_idx; A.aval = p->d_aval; A.nz_flags = p->d_nz_flags;
-    A.Y = p->d_Y; A.K = p->d_K; A.col_flags = p->d_col_flags;
-    A.n_groups = p->n_groups; A.total_rows = p->total_rows;
-
-    cudaStream_t s = p->stream;
-    const int64_t ng = std::max<int64_t>(p->n_groups, 1);
-    p->last_launches = 0;
-    CUDA_TRY(cudaEventRecord(p->ev_start, s));
-    CUDA_TRY(cudaMemsetAsync(p->d_ctrl, 0, sizeof(Ctrl), s));
-    CUDA_TRY(cudaMemsetAsync(p->d_iters, 0, sizeof(int32_t) * ng, s));
-    CUDA_TRY(cudaMemsetAsync(p->d_status, 0, sizeof(int32_t) * ng, s));
-    CUDA_TRY(cudaMemsetAsync(p->d_est, 0, sizeof(double) * std::max<int64_t>(3 * p->total_rows, 1), s));
-    CUDA_TRY(cudaMemsetAsync(p->d_info, 0, sizeof(PackInfo) * ng, s));
-    CUDA_TRY(cudaMemsetAsync(p->d_ginfo, 0, sizeof(GroupImg) * ng, s));
-    CUDA_TRY(cudaMemsetAsync(p->d_nnz_nonzero, 0, sizeof(int64_t) * ng, s));
-    CUDA_TRY(cudaEventRecord(p->ev_fork, s));
-    // pack + SELL, one bucket per stream
-    for (auto &b : p->buckets) {
-        CUDA_TRY(cudaStreamWaitEvent(b.stream, p->ev_fork, 0));
-        int rc = launch_pack(p, b, A);
-        if (rc) return rc;
-        CUDA_TRY(cudaStreamWaitEvent(s, b.ev1, 0));
-    }
-    if (!p->single_tx.empty()) {
-        size_t woff = 0;
-        for (auto &b : p->buckets) woff += b.work.size();
-        const int n = (int)p->single_tx.size();
-        pack_resident_kernel<64><<<n, 64, 0, s>>>(A, p->d_work_all + woff, n, p->d_img_off, p->d_img, p->d_info,
-                                                   p->d_nnz_nonzero, p->d_est, p->d_status, &p->d_ctrl->err, 1);
-        CUDA_TRY(cudaGetLastError());
-        p->last_launches += 1;
-    }
-    CUDA_TRY(cudaEventRecord(p->ev_packed, s));
-    // EM, one class per stream; the queues were filled on the device
-    if (!p->buckets.empty()) {
-        for (int c = kNumClasses - 1; c >= 0; --c) {
-            CUDA_TRY(cudaStreamWaitEvent(p->em_stream[c], p->ev_packed, 0));
-            int rc = launch_em(p, c, P);
-            if (rc) return rc;
-            CUDA_TRY(cudaEventRecord(p->em_done[c], p->em_stream[c]));
-            CUDA_TRY(cudaStreamWaitEvent(s, p->em_done[c], 0));
-        }
-    }
-    CUDA_TRY(cudaEventRecord(p->ev_end, s));
-    p->ran = true;
-    p->finished = false;
+    Slot &s = p->slot;
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    s.v_col_idx = d_col_idx; s.v_aval = d_aval; s.v_nz_flags = d_nz_flags;
+    s.v_Y = d_Y; s.v_K = d_K; s.v_col_flags = d_col_flags;
+    s.payload_bound = true;
+    s.payload_ready = true;
     return BAMBU_EM_OK;
 }
 
 int bambu_em_plan_run(bambu_em_plan *p, int32_t maxiter, double minvalue, double conv)
 {
     if (!p) return fail(BAMBU_EM_EINVAL, "plan is NULL");
-    if (!p->payload_ready) return fail(BAMBU_EM_ESTATE, "run before upload/bind_device");
-    if (conv != conv || minvalue != minvalue) return fail(BAMBU_EM_EINVAL, "conv/minvalue is NaN");
-    int rc = ensure_device();
-    if (rc) return rc;
-    p->last_maxiter = maxiter;
-    p->last_minvalue = minvalue;
-    p->last_conv = conv;
-    return enqueue_run(p);
-}
-
-// wait for the run; if the SELL pool was too small, grow it and run again
-static int finish_run(bambu_em_plan *p)
-{
-    for (int attempt = 0; attempt < 8; ++attempt) {
-        int err = 0;
-        CUDA_TRY(cudaMemcpyAsync(&err, &p->d_ctrl->err, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
-        CUDA_TRY(cudaStreamSynchronize(p->stream));
-        if (err == 0) { p->finished = true; return BAMBU_EM_OK; }
-        if (err == kErrColRange) return fail(BAMBU_EM_EINVAL, "col_idx outside its group's column range");
-        if (err == kErrColOrder) return fail(BAMBU_EM_EINVAL, "col_idx not strictly increasing inside a row");
-        if (err == kErrTooBig) return fail(BAMBU_EM_EINVAL, "a gene group's image exceeds the shared-memory resident tier");
-        if (err != kErrPool) return fail(BAMBU_EM_ECUDA, "device error word %d", err);
-        cudaFree(p->d_pool);
-        p->d_pool = nullptr;
-        p->device_bytes -= p->pool_bytes;
-        p->pool_bytes *= 2;
-        int rc = dev_alloc(p, &p->d_pool, (size_t)p->pool_bytes);
-        if (rc) return rc;
-        rc = enqueue_run(p);
-        if (rc) return rc;
-    }
-    return fail(BAMBU_EM_ENOMEM, "SELL image pool kept overflowing");
+    TRY(ensure_device());
+    return slot_run(p->slot, maxiter, minvalue, conv);
 }
 
 int bambu_em_plan_sync(bambu_em_plan *p)
 {
     if (!p) return fail(BAMBU_EM_EINVAL, "plan is NULL");
-    if (p->ran && !p->finished) return finish_run(p);
-    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    if (p->slot.ran && !p->slot.finished) return slot_finish(p->slot);
+    CUDA_TRY(cudaStreamSynchronize(p->slot.stream));
     return BAMBU_EM_OK;
 }
 
 int bambu_em_plan_download(bambu_em_plan *p, double *est, int32_t *iters, int32_t *status, int64_t *nnz_nonzero)
 {
     if (!p) return fail(BAMBU_EM_EINVAL, "plan is NULL");
-    if (!p->ran) return fail(BAMBU_EM_ESTATE, "download before run");
-    if (!p->finished) { int rc = finish_run(p); if (rc) return rc; }
-    cudaStream_t s = p->stream;
-    if (est && p->total_rows)
-        CUDA_TRY(cudaMemcpyAsync(est, p->d_est, sizeof(double) * 3 * p->total_rows, cudaMemcpyDeviceToHost, s));
-    if (iters && p->n_groups)
-        CUDA_TRY(cudaMemcpyAsync(iters, p->d_iters, sizeof(int32_t) * p->n_groups, cudaMemcpyDeviceToHost, s));
-    if (status && p->n_groups)
-        CUDA_TRY(cudaMemcpyAsync(status, p->d_status, sizeof(int32_t) * p->n_groups, cudaMemcpyDeviceToHost, s));
-    if (nnz_nonzero && p->n_groups)
-        CUDA_TRY(cudaMemcpyAsync(nnz_nonzero, p->d_nnz_nonzero, sizeof(int64_t) * p->n_groups, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    Slot &s = p->slot;
+    if (!s.ran) return fail(BAMBU_EM_ESTATE, "download before run");
+    TRY(slot_finish(s));
+    TRY(slot_download_async(s, est, s.rows(), iters, status, nnz_nonzero));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
     return BAMBU_EM_OK;
 }
 
@@ -644,16 +778,18 @@ int bambu_em_plan_download_live(bambu_em_plan *p, int32_t *live_cols, int32_t *l
                                 int32_t *slots)
 {
     if (!p) return fail(BAMBU_EM_EINVAL, "plan is NULL");
-    if (!p->ran) return fail(BAMBU_EM_ESTATE, "download before run");
-    if (!p->finished) { int rc = finish_run(p); if (rc) return rc; }
-    std::vector<PackInfo> h((size_t)p->n_groups);
-    std::vector<GroupImg> gi((size_t)p->n_groups);
-    if (p->n_groups) {
-        CUDA_TRY(cudaMemcpyAsync(h.data(), p->d_info, sizeof(PackInfo) * p->n_groups, cudaMemcpyDeviceToHost, p->stream));
-        CUDA_TRY(cudaMemcpyAsync(gi.data(), p->d_ginfo, sizeof(GroupImg) * p->n_groups, cudaMemcpyDeviceToHost, p->stream));
-        CUDA_TRY(cudaStreamSynchronize(p->stream));
+    Slot &s = p->slot;
+    if (!s.ran) return fail(BAMBU_EM_ESTATE, "download before run");
+    TRY(slot_finish(s));
+    const size_t ng = (size_t)s.ng();
+    std::vector<PackInfo> h(ng);
+    std::vector<GroupImg> gi(ng);
+    if (ng) {
+        CUDA_TRY(cudaMemcpyAsync(h.data(), s.info.p, sizeof(PackInfo) * ng, cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(cudaMemcpyAsync(gi.data(), s.ginfo.p, sizeof(GroupImg) * ng, cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(cudaStreamSynchronize(s.stream));
     }
-    for (int64_t g = 0; g < p->n_groups; ++g) {
+    for (size_t g = 0; g < ng; ++g) {
         if (live_cols) live_cols[g] = h[g].NL;
         if (live_nnz) live_nnz[g] = h[g].nnzL;
         if (smem_bytes) smem_bytes[g] = (int32_t)gi[g].smem_bytes;
@@ -665,22 +801,23 @@ int bambu_em_plan_download_live(bambu_em_plan *p, int32_t *live_cols, int32_t *l
 int bambu_em_plan_device_outputs(bambu_em_plan *p, double **d_est, int32_t **d_iters, int32_t **d_status)
 {
     if (!p) return fail(BAMBU_EM_EINVAL, "plan is NULL");
-    if (d_est) *d_est = p->d_est;
-    if (d_iters) *d_iters = p->d_iters;
-    if (d_status) *d_status = p->d_status;
+    if (d_est) *d_est = p->slot.est.as<double>();
+    if (d_iters) *d_iters = p->slot.iters.as<int32_t>();
+    if (d_status) *d_status = p->slot.status.as<int32_t>();
     return BAMBU_EM_OK;
 }
 
 int bambu_em_plan_last_run_ms(bambu_em_plan *p, float *pack_ms, float *em_ms, float *total_ms)
 {
     if (!p) return fail(BAMBU_EM_EINVAL, "plan is NULL");
-    if (!p->ran) return fail(BAMBU_EM_ESTATE, "no run yet");
-    if (!p->finished) { int rc = finish_run(p); if (rc) return rc; }
-    CUDA_TRY(cudaEventSynchronize(p->ev_end));
+    Slot &s = p->slot;
+    if (!s.ran) return fail(BAMBU_EM_ESTATE, "no run yet");
+    TRY(slot_finish(s));
+    CUDA_TRY(cudaEventSynchronize(s.ev_end));
     float pk = 0.f, em = 0.f, tot = 0.f;
-    CUDA_TRY(cudaEventElapsedTime(&pk, p->ev_start, p->ev_packed));
-    CUDA_TRY(cudaEventElapsedTime(&em, p->ev_packed, p->ev_end));
-    CUDA_TRY(cudaEventElapsedTime(&tot, p->ev_start, p->ev_end));
+    CUDA_TRY(cudaEventElapsedTime(&pk, s.ev_start, s.ev_packed));
+    CUDA_TRY(cudaEventElapsedTime(&em, s.ev_packed, s.ev_end));
+    CUDA_TRY(cudaEventElapsedTime(&tot, s.ev_start, s.ev_end));
     if (pack_ms) *pack_ms = pk;
     if (em_ms) *em_ms = em;
     if (total_ms) *total_ms = tot;
@@ -690,18 +827,36 @@ int bambu_em_plan_last_run_ms(bambu_em_plan *p, float *pack_ms, float *em_ms, fl
 int bambu_em_plan_last_run_launches(bambu_em_plan *p, int32_t *n)
 {
     if (!p || !n) return fail(BAMBU_EM_EINVAL, "NULL argument");
-    *n = p->last_launches;
+    *n = p->slot.launches;
     return BAMBU_EM_OK;
 }
 
 int bambu_em_plan_device_bytes(bambu_em_plan *p, int64_t *bytes)
 {
     if (!p || !bytes) return fail(BAMBU_EM_EINVAL, "NULL argument");
-    *bytes = p->device_bytes;
+    *bytes = p->slot.device_bytes;
     return BAMBU_EM_OK;
 }
 
-int bambu_em_shutdown(void) { return BAMBU_EM_OK; }
+// ---- one-shot: stream the arena through the cached three-slot pipeline ---------------
+static int64_t chunk_target_bytes()
+{
+    const char *e = getenv("BAMBU_EM_CHUNK_MB");
+    double mb = e ? atof(e) : 128.0;
+    if (!(mb > 0.0)) mb = 128.0;
+    return (int64_t)(mb * 1048576.0);
+}
+
+static int collect(Slot &s)   // finish a pipelined chunk: wait, (retry), download
+{
+    if (!s.busy) return BAMBU_EM_OK;
+    s.busy = false;
+    const bool had_to_wait = !s.finished;
+    TRY(slot_finish(s));
+    (void)had_to_wait;
+    TRY(slot_download_async(s, s.dl_est, s.dl_total_rows, s.dl_iters, s.dl_status, nullptr));
+    return BAMBU_EM_OK;
+}
 
 static int batched_impl(int64_t n_groups, const int64_t *grp_row_ptr, const int64_t *grp_col_ptr,
                         const int64_t *row_nnz_ptr, const int32_t *col_idx, const double *aval,
@@ -710,13 +865,46 @@ static int batched_impl(int64_t n_groups, const int64_t *grp_row_ptr, const int6
                         bool single_tx_shortcut)
 {
     if (!est || !iters || !status) return fail(BAMBU_EM_EINVAL, "NULL output pointer");
-    bambu_em_plan *p = nullptr;
-    int rc = plan_create_impl(&p, n_groups, grp_row_ptr, grp_col_ptr, row_nnz_ptr, single_tx_shortcut);
-    if (rc) return rc;
-    rc = bambu_em_plan_upload(p, col_idx, aval, nz_flags, Y, K, col_flags);
-    if (!rc) rc = bambu_em_plan_run(p, maxiter, minvalue, conv);
-    if (!rc) rc = bambu_em_plan_download(p, est, iters, status, nullptr);
-    bambu_em_plan_destroy(p);
+    TRY(check_arrays(n_groups, grp_row_ptr, grp_col_ptr, row_nnz_ptr));
+    TRY(ensure_device());
+    g_pipe_used = true;
+    const int64_t total_rows = grp_row_ptr[n_groups];
+    const int64_t target = chunk_target_bytes();
+    int rc = BAMBU_EM_OK;
+    int64_t g0 = 0;
+    int k = 0;
+    while (g0 < n_groups && !rc) {
+        // next chunk: groups until ~target bytes of arena
+        int64_t g1 = g0;
+        int64_t bytes = 0;
+        while (g1 < n_groups && (g1 == g0 || bytes < target)) {
+            const int64_t rows = grp_row_ptr[g1 + 1] - grp_row_ptr[g1], cols = grp_col_ptr[g1 + 1] - grp_col_ptr[g1];
+            const int64_t e = row_nnz_ptr[grp_row_ptr[g1 + 1]] - row_nnz_ptr[grp_row_ptr[g1]];
+            bytes += 13 * e + 17 * cols + 8 * rows + 16;
+            ++g1;
+        }
+        Slot &s = g_pipe[k % 3];
+        ++k;
+        rc = collect(s);                        // the slot's previous chunk (its D2H is then ordered on its stream)
+        if (rc) break;
+        s.single_tx_shortcut = single_tx_shortcut;
+        rc = slot_prepare(s, grp_row_ptr, grp_col_ptr, row_nnz_ptr, g0, g1);
+        if (!rc) rc = slot_upload(s, col_idx, aval, nz_flags, Y, K, col_flags);
+        if (!rc) rc = slot_run(s, maxiter, minvalue, conv);
+        if (!rc) {
+            s.busy = true;
+            s.dl_est = est; s.dl_iters = iters; s.dl_status = status; s.dl_total_rows = total_rows;
+        }
+        g0 = g1;
+    }
+    for (Slot &s : g_pipe) {
+        int rc2 = collect(s);
+        if (!rc) rc = rc2;
+    }
+    for (Slot &s : g_pipe)
+        if (s.inited && cudaStreamSynchronize(s.stream) != cudaSuccess && !rc)
+            rc = fail(BAMBU_EM_ECUDA, "pipeline stream failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (n_groups == 0) return BAMBU_EM_OK;
     return rc;
 }
 
@@ -740,8 +928,8 @@ int bambu_emWithL1(const double *A, const double *A_full, const double *A_unique
     std::vector<int64_t> grp_row{0, M}, grp_col{0, N}, rnp((size_t)M + 1, 0);
     std::vector<int32_t> ci;
     std::vector<double> av;
-    std::vector<uint8_t> nf, cf((size_t)N, 0);
-    std::vector<int8_t> col_seen((size_t)N, -1);   // -1 unknown, 0 unique kept, 1 multi
+    std::vector<uint8_t> nf, cf((size_t)N + 1, 0);
+    std::vector<int8_t> col_seen((size_t)N + 1, -1);   // -1 unknown, 0 unique kept, 1 multi
     for (int j = 0; j < N; ++j)
         for (int i = 0; i < M; ++i) {
             const double a = A[i + (size_t)j * M], u = A_unique[i + (size_t)j * M];

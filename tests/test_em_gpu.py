@@ -70,6 +70,19 @@ def test_larger_groups_exact(em, oracle_mod):
     check_against_oracle(em, oracle_mod, Arena.concatenate([a, b]))
 
 
+def test_batched_pipeline_many_chunks(em, oracle_mod, monkeypatch):
+    """bambu_em_batched streams the arena through three slots; tiny chunks force many
+    hand-overs (slot reuse, buffer growth, offsets into the caller's output arrays)."""
+    from bambu_b200 import synthetic
+    a = synthetic.config2(scale=0.05)
+    o_est, o_it, o_st = oracle_mod.em_batched(a, mode=oracle_mod.MODE_SPARSE)
+    for mb in ("1", "3", "0.2"):
+        monkeypatch.setenv("BAMBU_EM_CHUNK_MB", mb)
+        est, iters, status = em.abundance_quantification(a, maxiter=10000)
+        assert np.array_equal(iters, o_it) and np.array_equal(status, o_st)
+        assert_same_doubles(est, o_est, f"chunk {mb} MB")
+
+
 def test_config2_small_exact(em, oracle_mod):
     from bambu_b200 import synthetic
     a = synthetic.config2(scale=0.05)
@@ -136,7 +149,7 @@ def test_nan_poisoning_group(em, oracle_mod):
     assert iters[0] == 2 and status[0] & 2 and np.isnan(est[:, 2]).all()
 
 
-def test_empty_and_degenerate_inputs(em):
+def test_empty_and_degenerate_inputs(em, oracle_mod):
     from bambu_b200.arena import Arena
     z = np.zeros(1, np.int64)
     empty = Arena(z, z, z, np.zeros(0, np.int32), np.zeros(0), np.zeros(0, np.uint8), np.zeros(0), np.zeros(0),
@@ -145,14 +158,19 @@ def test_empty_and_degenerate_inputs(em):
     assert est.shape == (3, 0) and len(iters) == 0
     # a group without rows between two ordinary groups; a group whose columns are all unobserved
     rng = np.random.default_rng(2)
-    a = random_arena(rng, n_groups=3, single_tx_frac=0.0)
+    a = random_arena(rng, n_groups=3, single_tx_frac=0.0, zero_frac=0.0)
     a.grp_row_ptr = np.insert(a.grp_row_ptr, 1, a.grp_row_ptr[1])
     a.grp_col_ptr = np.insert(a.grp_col_ptr, 1, a.grp_col_ptr[1])
-    est, iters, status = em.abundance_quantification(a)
+    est, iters, status = check_against_oracle(em, oracle_mod, a)
     assert iters[1] == 0 and np.isfinite(est).all()
     a.Y[:] = 0.0
-    est, iters, status = em.abundance_quantification(a)
+    est, iters, status = check_against_oracle(em, oracle_mod, a)
     assert (est == 0).all() and (iters[[0, 2, 3]] == 1).all()
+    # explicit zeros: a column whose only entry is an explicit zero has colsum 0 with Y > 0 ->
+    # baseSum = inf -> the dense reference turns every row of the group into NaN (0 * inf)
+    b = random_arena(np.random.default_rng(2), n_groups=3, single_tx_frac=0.0)
+    est, iters, status = check_against_oracle(em, oracle_mod, b)
+    assert np.isnan(est).any() and (status & 2).any()
 
 
 def test_malformed_arena_is_rejected(em):
