@@ -21,6 +21,7 @@
 #include "../../include/bambu_em.h"
 #include "common.cuh"
 #include "em_sell.cuh"
+#include "giant.cuh"
 #include "pack_kernel.cuh"
 #include "sell_kernel.cuh"
 
@@ -118,6 +119,7 @@ struct Ctrl {   // device control block, zeroed at the start of every run
     unsigned long long pool_ctr;
     int qcount[8];
     int ticket[8];
+    unsigned int gflags[8];   // streamed tier: hazard flags, inf-column count, non-finite flag
 };
 
 // ------------------------------------------------------------------------------
@@ -184,7 +186,13 @@ struct Slot {
     bool single_tx_shortcut = true;   // R/bambu-quantify_utilityFunctions.R:410-414 (run_parallel, not emWithL1)
     // device buffers (grow-only)
     DevBuf grp_row_ptr, grp_col_ptr, row_nnz_ptr, payload, img, img_off, info, pool, ginfo, queue, nnz_nonzero, est,
-        iters, status, work, ctrl;
+        iters, status, work, ctrl, gdesc, gbuf;
+    // streamed tier (giant loci) of the current chunk
+    int n_giant = 0;
+    uint32_t giant_smem = 0;
+    PinBuf h_gdesc;
+    cudaStream_t giant_stream = nullptr;
+    cudaEvent_t giant_packed = nullptr;
     int64_t pool_bytes = 0;
     // payload views (device, already shifted so that absolute arena indices work)
     bool payload_bound = false, payload_ready = false;
@@ -231,6 +239,8 @@ static int slot_init(Slot &s)
         CUDA_TRY(cudaStreamCreateWithFlags(&s.buckets[b].stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&s.buckets[b].done, cudaEventDisableTiming));
     }
+    CUDA_TRY(cudaStreamCreateWithFlags(&s.giant_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&s.giant_packed, cudaEventDisableTiming));
     s.inited = true;
     return BAMBU_EM_OK;
 }
@@ -246,12 +256,14 @@ static void slot_destroy(Slot &s)
         if (s.em_stream[c]) { cudaStreamSynchronize(s.em_stream[c]); cudaStreamDestroy(s.em_stream[c]); }
         if (s.em_done[c]) cudaEventDestroy(s.em_done[c]);
     }
-    for (cudaEvent_t e : {s.ev_start, s.ev_fork, s.ev_packed, s.ev_end, s.ev_free})
+    if (s.giant_stream) { cudaStreamSynchronize(s.giant_stream); cudaStreamDestroy(s.giant_stream); }
+    for (cudaEvent_t e : {s.ev_start, s.ev_fork, s.ev_packed, s.ev_end, s.ev_free, s.giant_packed})
         if (e) cudaEventDestroy(e);
     if (s.own_stream) cudaStreamDestroy(s.own_stream);
     for (DevBuf *b : {&s.grp_row_ptr, &s.grp_col_ptr, &s.row_nnz_ptr, &s.payload, &s.img, &s.img_off, &s.info, &s.pool,
-                      &s.ginfo, &s.queue, &s.nnz_nonzero, &s.est, &s.iters, &s.status, &s.work, &s.ctrl})
+                      &s.ginfo, &s.queue, &s.nnz_nonzero, &s.est, &s.iters, &s.status, &s.work, &s.ctrl, &s.gdesc, &s.gbuf})
         b->release();
+    s.h_gdesc.release();
     s.h_img_off.release();
     s.h_work.release();
     s = Slot();
@@ -288,9 +300,19 @@ static int pack_config_T()
     return BAMBU_EM_OK;
 }
 
+constexpr int kGiantThreads = 1024;
+static int g_giant_grid_per_sm = 0;
+
+static bool force_giant()
+{
+    const char *e = getenv("BAMBU_EM_FORCE_GIANT");
+    return e && e[0] == '1';
+}
+
 static int configure_kernels()
 {
     if (g_em_configured) return BAMBU_EM_OK;
+    CUDA_TRY(cudaFuncSetAttribute(em_giant_kernel<kGiantThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     for (int c = 0; c < kNumClasses; ++c) {
         switch (kEmClasses[c].threads) {
         case 64: TRY(em_config_T<64>(c)); break;
@@ -418,7 +440,10 @@ static int slot_prepare(Slot &s, const int64_t *grp_row_ptr, const int64_t *grp_
     std::vector<int32_t> single;
     std::vector<int64_t> gnnz((size_t)ng, 0);
     uint32_t smem_pack[8] = {}, smem_sell[8] = {};
-    int64_t off = 0;
+    int64_t off = 0, goff = 0;
+    std::vector<GiantDesc> giants;
+    uint32_t gsmem = 0;
+    const bool forced_giant = force_giant();
     for (int64_t g = g0; g < g1; ++g) {
         const int64_t M = grp_row_ptr[g + 1] - grp_row_ptr[g], N = grp_col_ptr[g + 1] - grp_col_ptr[g];
         if (M < 0 || N < 0) return fail(BAMBU_EM_EINVAL, "group %lld has negative extent", (long long)g);
@@ -428,10 +453,21 @@ static int slot_prepare(Slot &s, const int64_t *grp_row_ptr, const int64_t *grp_
         if (M == 0) continue;
         if (M == 1 && s.single_tx_shortcut) { single.push_back((int32_t)g); continue; }
         const double ub = 20.0 * (double)e + 18.0 * (double)(M + N) + 64.0;
-        if (M > kMaxIndex || N > kMaxIndex || ub > (double)kSmemMax)
-            return fail(BAMBU_EM_EINVAL,
-                        "group %lld (M=%lld N=%lld entries=%lld) exceeds the shared-memory resident tier",
-                        (long long)g, (long long)M, (long long)N, (long long)e);
+        if (M > kMaxIndex || N > kMaxIndex || ub > (double)kSmemMax || forced_giant) {
+            // streamed tier: image in global memory, all SMs iterate on this one group
+            if (8 * M > (int64_t)kSmemMax || M > INT32_MAX / 8 || N > INT32_MAX / 2 || e > (int64_t)UINT32_MAX - 64)
+                return fail(BAMBU_EM_EINVAL, "group %lld (M=%lld N=%lld entries=%lld) exceeds the streamed tier",
+                            (long long)g, (long long)M, (long long)N, (long long)e);
+            GiantDesc d;
+            memset(&d, 0, sizeof d);
+            d.g = (int32_t)g; d.M = (int32_t)M; d.N = (int32_t)N;
+            giant_layout(d, M, N, e);
+            d.base = goff;
+            goff += d.total;
+            giants.push_back(d);
+            gsmem = std::max<uint32_t>(gsmem, (uint32_t)(8 * M));
+            continue;
+        }
         const uint32_t bytes = em_smem_bytes((uint32_t)M, (uint32_t)N, (uint32_t)e);
         int c = 0;
         while (c < kNumPackClasses - 1 && bytes > kPackClasses[c].max_bytes) ++c;
@@ -481,8 +517,18 @@ static int slot_prepare(Slot &s, const int64_t *grp_row_ptr, const int64_t *grp_
     TRY(s.iters.ensure(4 * (size_t)ng, &s.device_bytes));
     TRY(s.status.ensure(4 * (size_t)ng, &s.device_bytes));
     TRY(s.ctrl.ensure(sizeof(Ctrl), &s.device_bytes));
+    s.n_giant = (int)giants.size();
+    s.giant_smem = gsmem;
+    if (s.n_giant) {
+        TRY(s.h_gdesc.ensure(sizeof(GiantDesc) * giants.size()));
+        memcpy(s.h_gdesc.p, giants.data(), sizeof(GiantDesc) * giants.size());
+        TRY(s.gdesc.ensure(sizeof(GiantDesc) * giants.size(), &s.device_bytes));
+        TRY(s.gbuf.ensure((size_t)goff, &s.device_bytes));
+    }
 
     cudaStream_t st = s.stream;
+    if (s.n_giant)
+        CUDA_TRY(cudaMemcpyAsync(s.gdesc.p, s.h_gdesc.p, sizeof(GiantDesc) * giants.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(s.grp_row_ptr.p, grp_row_ptr + g0, 8 * (size_t)(ng + 1), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(s.grp_col_ptr.p, grp_col_ptr + g0, 8 * (size_t)(ng + 1), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(s.row_nnz_ptr.p, row_nnz_ptr + s.r0, 8 * (size_t)(rows + 1), cudaMemcpyHostToDevice, st));
@@ -557,6 +603,15 @@ static int slot_enqueue(Slot &s)
         CUDA_TRY(cudaGetLastError());
         s.launches += 1;
     }
+    if (s.n_giant) {   // streamed tier: pack now (one CTA per giant group), iterate after the resident classes
+        CUDA_TRY(cudaStreamWaitEvent(s.giant_stream, s.ev_fork, 0));
+        pack_giant_kernel<1024><<<s.n_giant, 1024, 0, s.giant_stream>>>(v.A, s.gdesc.as<GiantDesc>(), s.n_giant,
+                                                                         s.gbuf.as<uint8_t>(), v.nnz_nonzero, &v.ctrl->err);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(s.giant_packed, s.giant_stream));
+        CUDA_TRY(cudaStreamWaitEvent(st, s.giant_packed, 0));
+        s.launches += 1;
+    }
     CUDA_TRY(cudaEventRecord(s.ev_packed, st));
     if (any) {   // EM, one class per stream; the queues were filled on the device
         for (int c = kNumClasses - 1; c >= 0; --c) {
@@ -565,6 +620,36 @@ static int slot_enqueue(Slot &s)
             CUDA_TRY(cudaEventRecord(s.em_done[c], s.em_stream[c]));
             CUDA_TRY(cudaStreamWaitEvent(st, s.em_done[c], 0));
         }
+    }
+    if (s.n_giant) {
+        // cooperative launch: every CTA must be resident at once, so this runs after the resident
+        // classes have drained (ordered on the main stream)
+        if (!g_giant_grid_per_sm) {
+            int per_sm = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_giant_kernel<kGiantThreads>, kGiantThreads,
+                                                                   (size_t)kSmemMax));
+            if (per_sm < 1) return fail(BAMBU_EM_ECUDA, "streamed EM kernel does not fit an SM");
+            g_giant_grid_per_sm = per_sm;
+        }
+        const GiantDesc *descs = s.gdesc.as<GiantDesc>();
+        int n_giant = s.n_giant;
+        const uint8_t *gbuf_c = s.gbuf.as<uint8_t>();
+        uint8_t *gbuf = s.gbuf.as<uint8_t>();
+        const int64_t *grp = v.A.grp_row_ptr;
+        int64_t rows = s.rows();
+        EmParams P = s.P;
+        double *est = v.est;
+        int32_t *iters = v.iters, *status = v.status;
+        unsigned int *gflags = v.ctrl->gflags;
+        void *args[] = {&descs, &n_giant, &gbuf_c, &gbuf, &grp, &rows, &P, &est, &iters, &status, &gflags};
+        // dynamic shared memory: one private copy of theta per CTA
+        const size_t smem = std::max<size_t>(s.giant_smem, 1024);
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_giant_kernel<kGiantThreads>, kGiantThreads, smem));
+        per_sm = std::max(1, std::min(per_sm, 2));
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void *)em_giant_kernel<kGiantThreads>, dim3(g_num_sms * per_sm),
+                                             dim3(kGiantThreads), args, smem, st));
+        s.launches += 1;
     }
     CUDA_TRY(cudaEventRecord(s.ev_end, st));
     s.ran = true;

@@ -44,7 +44,7 @@ def assert_same_doubles(a, b, what=""):
 
 
 def random_arena(rng, n_groups=20, max_m=40, max_n=80, density=0.15, zero_frac=0.05, dead_col_frac=0.5,
-                 single_tx_frac=0.1, d_like=True):
+                 single_tx_frac=0.1, d_like=True, no_empty_cols=False):
     """Random arena with the edge cases the EM must survive: explicit zeros,
     columns with Y == 0, single-transcript groups, rows sharing columns."""
     from bambu_b200.arena import Arena
@@ -54,6 +54,8 @@ def random_arena(rng, n_groups=20, max_m=40, max_n=80, density=0.15, zero_frac=0
         N = int(rng.integers(1, max_n + 1))
         mask = rng.random((M, N)) < density
         mask[np.arange(M), rng.integers(0, N, M)] = True      # every row has an entry
+        if no_empty_cols:
+            mask[rng.integers(0, M, N), np.arange(N)] = True
         vals = np.where(rng.random((M, N)) < 0.4, 1.0, rng.uniform(0.01, 0.6, (M, N))) if d_like else np.ones((M, N))
         A = np.where(mask, vals, 0.0)
         eq = mask & (rng.random((M, N)) < 0.3)

@@ -158,7 +158,7 @@ def test_empty_and_degenerate_inputs(em, oracle_mod):
     assert est.shape == (3, 0) and len(iters) == 0
     # a group without rows between two ordinary groups; a group whose columns are all unobserved
     rng = np.random.default_rng(2)
-    a = random_arena(rng, n_groups=3, single_tx_frac=0.0, zero_frac=0.0)
+    a = random_arena(rng, n_groups=3, single_tx_frac=0.0, zero_frac=0.0, no_empty_cols=True)
     a.grp_row_ptr = np.insert(a.grp_row_ptr, 1, a.grp_row_ptr[1])
     a.grp_col_ptr = np.insert(a.grp_col_ptr, 1, a.grp_col_ptr[1])
     est, iters, status = check_against_oracle(em, oracle_mod, a)
@@ -166,8 +166,8 @@ def test_empty_and_degenerate_inputs(em, oracle_mod):
     a.Y[:] = 0.0
     est, iters, status = check_against_oracle(em, oracle_mod, a)
     assert (est == 0).all() and (iters[[0, 2, 3]] == 1).all()
-    # explicit zeros: a column whose only entry is an explicit zero has colsum 0 with Y > 0 ->
-    # baseSum = inf -> the dense reference turns every row of the group into NaN (0 * inf)
+    # an observed column without a non-zero entry has colsum 0 with Y > 0 -> baseSum = inf ->
+    # the dense reference turns every row of the group into NaN (0 * inf)
     b = random_arena(np.random.default_rng(2), n_groups=3, single_tx_frac=0.0)
     est, iters, status = check_against_oracle(em, oracle_mod, b)
     assert np.isnan(est).any() and (status & 2).any()
@@ -222,3 +222,58 @@ def test_plan_api_resident_runs_and_torch_buffers(em, oracle_mod):
         est, iters, status = plan.download()
         assert np.array_equal(iters, o_it)
         assert_same_doubles(est, o_est, "bound est")
+
+
+# ---------------------------------------------------------------- streamed tier (giant loci)
+@pytest.mark.parametrize("seed", range(3))
+def test_streamed_tier_forced_on_random_groups(em, oracle_mod, monkeypatch, seed):
+    """Every group through the multi-CTA cooperative path (normally reserved for giant
+    loci): same doubles, same iteration counts as the oracle, edge cases included."""
+    monkeypatch.setenv("BAMBU_EM_FORCE_GIANT", "1")
+    rng = np.random.default_rng(2000 + seed)
+    a = random_arena(rng, n_groups=25, max_m=70, max_n=150)
+    check_against_oracle(em, oracle_mod, a)
+    for par in ({"maxiter": 2}, {"conv": 1.0}, {"conv": 1e-5}, {"minvalue": 0.3}):
+        check_against_oracle(em, oracle_mod, a, **par)
+
+
+def giant_locus_arena(rng, M, N, k_mean, observed=0.4):
+    from bambu_b200.arena import Arena
+    k = 1 + rng.binomial(M - 1, k_mean / M, N)
+    cols = np.repeat(np.arange(N), k)
+    rows = rng.integers(0, M, len(cols))
+    key = np.unique(rows.astype(np.int64) * N + cols)
+    rows, cols = key // N, key % N
+    aval = np.where(rng.random(len(key)) < 0.3, 1.0, rng.uniform(0.02, 0.3, len(key)))
+    nobs = np.where(rng.random(N) < observed, 1.0 + rng.negative_binomial(0.5, 0.5 / 40.5, N), 0.0)
+    K = nobs.sum()
+    multi = np.bincount(cols, minlength=N) > 1
+    rnp = np.concatenate(([0], np.cumsum(np.bincount(rows, minlength=M)))).astype(np.int64)
+    return Arena(np.array([0, M], np.int64), np.array([0, N], np.int64), rnp, cols.astype(np.int32), aval,
+                 (rng.random(len(key)) < 0.2).astype(np.uint8), nobs / K, np.full(N, K), multi.astype(np.uint8),
+                 np.arange(M, dtype=np.int32))
+
+
+def test_giant_locus_matches_oracle(em, oracle_mod):
+    """One locus far beyond shared memory (400 transcripts x 30k read classes, ~600k entries)
+    next to ordinary groups; maxiter bounds the oracle's run time."""
+    from bambu_b200.arena import Arena
+    rng = np.random.default_rng(77)
+    big = giant_locus_arena(rng, 400, 30_000, 19.0)
+    small = random_arena(rng, n_groups=30)
+    a = Arena.concatenate([small, big, random_arena(rng, n_groups=10)])
+    est, iters, status = check_against_oracle(em, oracle_mod, a, maxiter=400)
+    assert iters[30] > 20
+
+
+def test_config3_scaled(em, oracle_mod):
+    """BASELINE.json configs[2] shape, scaled: ordinary genes + giant loci in one arena."""
+    from bambu_b200 import synthetic
+    ann = synthetic.annotation_for("config3", scale=0.04)      # 200 genes incl. 2 giant loci
+    a = synthetic.sample_arena(ann, 0)
+    M, N, e = a.group_shapes()
+    assert e.max() > 1_000_000
+    est, iters, status = check_against_oracle(em, oracle_mod, a, maxiter=150)
+    got = np.bincount(np.repeat(np.arange(a.n_groups), M), weights=est[0], minlength=a.n_groups)
+    want = np.bincount(np.repeat(np.arange(a.n_groups), N), weights=a.K * a.Y, minlength=a.n_groups)
+    assert np.allclose(got, want, rtol=1e-9)
