@@ -7,16 +7,18 @@ from bambu_b200.em import EmPlan, abundance_quantification
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 nsamp = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-ann = S.annotation_for("config2", scale=scale)
+cfg = sys.argv[3] if len(sys.argv) > 3 else "config2"
+maxiter = int(sys.argv[4]) if len(sys.argv) > 4 else 10000
+ann = S.annotation_for(cfg, scale=scale)
 t = time.time()
-arenas = [S.cohort_sample(ann, s) for s in range(nsamp)]
+arenas = [S.cohort_sample(ann, s) if cfg != "config3" else S.sample_arena(ann, s) for s in range(nsamp)]
 from bambu_b200.arena import Arena
 a = Arena.concatenate(arenas) if nsamp > 1 else arenas[0]
 print("gen %.1fs groups %d nnz %d bytes %.1f MB" % (time.time() - t, a.n_groups, a.nnz, a.nbytes() / 1e6))
 with EmPlan(a) as plan:
     plan.upload()
     for rep in range(4):
-        plan.run()
+        plan.run(maxiter=maxiter)
         plan.sync()
         ms = plan.last_run_ms()
         print("run", rep, ms)
@@ -30,5 +32,5 @@ with EmPlan(a) as plan:
 t = time.time()
 for rep in range(3):
     t = time.time()
-    abundance_quantification(a)
+    abundance_quantification(a, maxiter=maxiter)
     print("one-shot host call %.1f ms" % ((time.time() - t) * 1e3))
