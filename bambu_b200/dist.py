@@ -69,3 +69,40 @@ def gather_estimates(est, device=None, dst=0, group=None):
     if rank != dst:
         return None
     return [b[:, :n].cpu().numpy() for b, n in zip(bufs, all_rows)]
+
+
+class EstimateGatherer:
+    """Reusable gather of per-rank ``est[3, rows_r]`` tables to ``dst``: device staging
+    buffers and the pinned host result are allocated once (cohort steps repeat the same
+    shapes).  ``__call__`` takes this rank's pinned host table and returns, on ``dst``, a
+    list of pinned host tensors (views, overwritten by the next call)."""
+
+    def __init__(self, rows_local: int, device, dst: int = 0, group=None):
+        import torch
+        import torch.distributed as dist
+        self.dist, self.torch, self.group, self.dst = dist, torch, group, dst
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.device = torch.device(device)
+        rows = torch.tensor([rows_local], dtype=torch.int64, device=self.device)
+        allr = [torch.zeros_like(rows) for _ in range(self.world)]
+        dist.all_gather(allr, rows, group=group)
+        self.rows = [int(x) for x in allr]
+        self.max_rows = max(self.rows)
+        self.send = torch.zeros((3, self.max_rows), dtype=torch.float64, device=self.device)
+        self.recv = self.host = None
+        if self.rank == dst:
+            self.recv = [torch.empty_like(self.send) for _ in range(self.world)]
+            pin = self.device.type == "cuda"
+            self.host = [torch.empty((3, n), dtype=torch.float64, pin_memory=pin) for n in self.rows]
+
+    def __call__(self, est_host):
+        t = est_host if isinstance(est_host, self.torch.Tensor) else self.torch.from_numpy(est_host)
+        self.send[:, :t.shape[1]].copy_(t, non_blocking=True)
+        self.dist.gather(self.send, self.recv, dst=self.dst, group=self.group)
+        if self.rank != self.dst:
+            return None
+        for h, d, n in zip(self.host, self.recv, self.rows):
+            h.copy_(d[:, :n], non_blocking=True)
+        if self.device.type == "cuda":
+            self.torch.cuda.current_stream(self.device).synchronize()
+        return self.host

@@ -138,7 +138,8 @@ def run_reference(args):
     import oracle
     oracle.build()
     sub, n_all = bounded_cpu_sample(args.scale, args.cpu_frac)
-    work, secs, cores = cpu_reference(sub, oracle.MODE_DENSE_TRACE, args.steps, args.warmup)
+    # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
+    work, secs, cores = cpu_reference(sub, oracle.MODE_DENSE_TRACE, args.steps, args.warmup, threads=os.cpu_count() or 1)
     value = work * args.steps / secs
     sample = (f"{sub.n_groups} of the {n_all} gene groups of cohort sample 0 (random 1/{args.cpu_frac:g}), "
               f"{int(sub.group_nonzeros().sum())} non-zeros, per step")
@@ -247,11 +248,15 @@ def run_b200(args):
     value = work_all * args.steps / (ms * 1e-3)
 
     # ---- end to end through the C-ABI with host buffers ------------------------------------
+    gatherer = None
+    if world > 1:     # outputs to rank 0 (the reference's combineCountSes cbind, R/bambu_utilityFunctions.R:215-241)
+        from bambu_b200.dist import EstimateGatherer
+        gatherer = EstimateGatherer(rows, dev)
+
     def e2e_step():
         abundance_quantification_into(arena, h_est.numpy(), h_iters.numpy(), h_status.numpy(), **EM_PAR)
-        if world > 1:     # outputs to rank 0 (the reference's combineCountSes cbind, R/bambu_utilityFunctions.R:215-241)
-            from bambu_b200.dist import gather_estimates
-            gather_estimates(h_est, dev)
+        if gatherer is not None:
+            gatherer(h_est)
     for _ in range(min(args.warmup, 2)):
         e2e_step()
     barrier()
@@ -294,7 +299,7 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                         "kernel": "em_resident_kernel (all size buckets; pack kernels included in the time)",
+                         "kernel": "em_sell_kernel (all size classes; pack + SELL kernels included in the time)",
                          "algorithmic_bytes": "24 B x nnz_g x iters_g (SURVEY 8d streaming-equivalent); the resident "
                                               "tier keeps the slice in shared memory, so HBM traffic is far below this",
                          "achieved_live": ALG_BYTES_PER_NNZ_ITER * (live_all / world) / step_s / 1e9,
@@ -309,8 +314,8 @@ def run_b200(args):
             oracle.build()
             sub = arena.select_groups(np.sort(np.random.default_rng(0).choice(
                 int(arena.sample_grp_ptr[1]), max(1, int(arena.sample_grp_ptr[1] / args.cpu_frac)), replace=False)))
-            w1, s1, cores = cpu_reference(sub, oracle.MODE_DENSE_TRACE, 1, 0)
-            w2, s2, _ = cpu_reference(sub, oracle.MODE_SPARSE, 3, 1)
+            w1, s1, cores = cpu_reference(sub, oracle.MODE_DENSE_TRACE, 1, 0, threads=os.cpu_count() or 1)
+            w2, s2, _ = cpu_reference(sub, oracle.MODE_SPARSE, 3, 1, threads=os.cpu_count() or 1)
             line["cpu_baseline"] = {
                 "value": w1 / s1, "unit": "nnz-iterations/s", "cores": cores, "kind": "port",
                 "sample": f"{sub.n_groups} of the {int(arena.sample_grp_ptr[1])} gene groups of cohort sample 0 "

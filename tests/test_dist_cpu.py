@@ -40,7 +40,10 @@ def _worker(rank, world, port, q):
     mine = a.select_groups(shards[rank])
     est, iters, status = oracle.em_batched(mine, mode=oracle.MODE_SPARSE)
     got = bdist.gather_estimates(est)
+    g2 = bdist.EstimateGatherer(est.shape[1], "cpu")
+    got2 = g2(np.ascontiguousarray(est))
     if rank == 0:
+        assert all(np.array_equal(a, b.numpy(), equal_nan=True) for a, b in zip(got, got2))
         full_est, full_it, _ = oracle.em_batched(a, mode=oracle.MODE_SPARSE)
         M, _, _ = a.group_shapes()
         ok = True
