@@ -9,7 +9,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbambu_em.so")
+LIB_PATH = os.environ.get("BAMBU_EM_LIB") or os.path.join(_HERE, "libbambu_em.so")   # override: kernel experiments
 _lib = None
 
 OK, EINVAL, ENODEVICE, ECUDA, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5

@@ -453,7 +453,7 @@ static int slot_prepare(Slot &s, const int64_t *grp_row_ptr, const int64_t *grp_
         if (M == 0) continue;
         if (M == 1 && s.single_tx_shortcut) { single.push_back((int32_t)g); continue; }
         const double ub = 20.0 * (double)e + 18.0 * (double)(M + N) + 64.0;
-        if (M > kMaxIndex || N > kMaxIndex || ub > (double)kSmemMax || forced_giant) {
+        if (M > kMaxIndex || N > kMaxIndex || M + N > kMaxVecElems || ub > (double)kSmemMax || forced_giant) {
             // streamed tier: image in global memory, all SMs iterate on this one group
             if (8 * M > (int64_t)kSmemMax || M > INT32_MAX / 8 || N > INT32_MAX / 2 || e > (int64_t)UINT32_MAX - 64)
                 return fail(BAMBU_EM_EINVAL, "group %lld (M=%lld N=%lld entries=%lld) exceeds the streamed tier",

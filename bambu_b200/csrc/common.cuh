@@ -90,7 +90,9 @@ __host__ __device__ inline uint32_t pack_smem_bytes(uint32_t M, uint32_t N)
 // a loop whose trip count is uniform (no divergence, no parity branch).
 //
 //   [rs f64 M][Yl f64 NL]
-//   [row side : slotsR x {valE f64 x32 | valO f64 x32 | idxE u16 x32 | idxO u16 x32}]   640 B / slot
+//   [row side : slotsR x {(valE, valO) f64x2 x32 | offE u16 x32 | offO u16 x32}]        640 B / slot
+//               (an index is stored as the byte offset of the gathered element in the EM
+//                kernel's vector region -- theta[M+1] then ratio[NL+1] -- so 8*(M+NL+2) < 65536)
 //   [col side : slotsC x {same}]
 //   [rowid u16 32*nSliceR][colid u16 32*nSliceC][startR u32 nSliceR+1][startC u32 nSliceC+1]
 //                                                                   <- copied to shared memory
@@ -118,7 +120,7 @@ __host__ __device__ inline SellLayout sell_layout(uint32_t M, uint32_t NL, uint3
     SellLayout L;
     L.rs = 0;
     L.Yl = 8u * M;
-    L.sideR = L.Yl + 8u * NL;
+    L.sideR = align_up(L.Yl + 8u * NL, 16);   // slots are read as double2
     L.sideC = L.sideR + kSlotBytes * slotsR;
     L.rowid = L.sideC + kSlotBytes * slotsC;
     L.colid = L.rowid + 64u * nSliceR;
@@ -132,9 +134,12 @@ __host__ __device__ inline SellLayout sell_layout(uint32_t M, uint32_t NL, uint3
     return L;
 }
 
+// vector region of the EM kernel: theta[M+1] | ratio[NL+1]
+__host__ __device__ inline uint32_t sell_vec_bytes(uint32_t M, uint32_t NL) { return align_up(8u * (M + NL + 2), 16); }
+
 __host__ __device__ inline uint32_t sell_smem_bytes(const SellLayout &L, uint32_t M, uint32_t NL)
 {
-    return L.copy_bytes + 8u * (M + 1) + 8u * (NL + 1);
+    return sell_vec_bytes(M, NL) + L.copy_bytes;
 }
 
 // shared-memory scratch of the SELL builder for a group (lengths, ids, slice starts, histogram)
@@ -146,6 +151,7 @@ __host__ __device__ inline uint32_t sell_scratch_bytes(uint32_t M, uint32_t N)
 constexpr int kNumClasses = 6;
 constexpr uint32_t kSmemMax = 227u * 1024u - 256u;  // per-CTA opt-in maximum minus static shared
 constexpr int kMaxIndex = 32767;                    // u16 index carries a parity bit
+constexpr int kMaxVecElems = 8190;                  // M + NL of a resident group: byte offsets must fit u16
 
 // error codes written to the device error word by the kernels
 constexpr int kErrColRange = 1;   // col_idx outside [0, N)

@@ -10,12 +10,23 @@
 // one live column in the E-phase and one row in the M-phase; a warp owns slices of 32;
 // a CTA owns one group at a time and pulls groups from its class's queue.
 //
+// Shared memory: [theta f64 M+1][ratio f64 NL+1][image].  The image stores every index as
+// the byte offset of the gathered element in that vector region, so a gather needs no
+// address arithmetic.  theta[M] and ratio[NL] are always 0.0: padding entries (value 0.0)
+// point there and add an exact +0.0.
+//
 // FP64 throughout; products and sums use the non-contracting intrinsics: the reference
 // rounds a_ij*theta_i before it is summed (src/em.cpp:46-47), so no FMA may be formed.
 #pragma once
 #include "common.cuh"
 
+#ifndef BAMBU_V_UNROLL
+#define BAMBU_V_UNROLL 2
+#endif
+
 namespace bambu {
+
+constexpr int kSlotUnroll = BAMBU_V_UNROLL;   // slots of a line in flight per lane
 
 struct EmParams {
     int32_t maxiter;
@@ -27,23 +38,31 @@ __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000
 
 // sum over one line of a SELL side: a1 = even stream, a2 = odd stream.
 // MODE 0: plain; MODE 1: also count gathered elements that are not finite.
+__device__ __forceinline__ double vec_at(const uint8_t *vec, uint32_t off)
+{
+    return *reinterpret_cast<const double *>(vec + off);
+}
+
 template <int MODE>
 __device__ __forceinline__ void line_sums(const uint8_t *__restrict__ side, uint32_t s0, uint32_t s1, int lane,
-                                          const double *__restrict__ vec, double &a1, double &a2, int &cnt)
+                                          const uint8_t *__restrict__ vec, double &a1, double &a2, int &cnt)
 {
     const uint8_t *p = side + (size_t)kSlotBytes * s0;
-#pragma unroll 2
+#pragma unroll kSlotUnroll
     for (uint32_t s = s0; s < s1; ++s, p += kSlotBytes) {
-        const double ve = reinterpret_cast<const double *>(p)[lane];
-        const double vo = reinterpret_cast<const double *>(p + 256)[lane];
-        const uint32_t ie = reinterpret_cast<const uint16_t *>(p + 512)[lane];
-        const uint32_t io = reinterpret_cast<const uint16_t *>(p + 576)[lane];
-        const double xe = vec[ie], xo = vec[io];
+        const double2 v = reinterpret_cast<const double2 *>(p)[lane];
+        const uint32_t oe = reinterpret_cast<const uint16_t *>(p + 512)[lane];
+        const uint32_t oo = reinterpret_cast<const uint16_t *>(p + 576)[lane];
+        const double xe = vec_at(vec, oe), xo = vec_at(vec, oo);
         if (MODE == 1) cnt += (!is_finite(xe)) + (!is_finite(xo));
-        a1 = __dadd_rn(a1, __dmul_rn(ve, xe));
-        a2 = __dadd_rn(a2, __dmul_rn(vo, xo));
+        a1 = __dadd_rn(a1, __dmul_rn(v.x, xe));
+        a2 = __dadd_rn(a2, __dmul_rn(v.y, xo));
     }
 }
+
+#ifndef BAMBU_V_LAZY
+#define BAMBU_V_LAZY 1
+#endif
 
 template <int T>
 __global__ void __launch_bounds__(T)
@@ -73,22 +92,26 @@ em_sell_kernel(const int32_t *__restrict__ queue, const int *__restrict__ qcount
         const uint8_t *gimg = pool + ((size_t)gi.off16 << 4);
         const int64_t row0 = grp_row_ptr[g];
 
+        const uint32_t vec_bytes = sell_vec_bytes((uint32_t)M, (uint32_t)NL);
+        const uint8_t *vec = smem;                       // theta[M+1] | ratio[NL+1]
+        uint8_t *simg = smem + vec_bytes;
+
         // ---- image -> shared memory ------------------------------------------------
         {
             const uint4 *src = reinterpret_cast<const uint4 *>(gimg);
-            uint4 *dst = reinterpret_cast<uint4 *>(smem);
+            uint4 *dst = reinterpret_cast<uint4 *>(simg);
             const int n16 = (int)(L.copy_bytes >> 4);
             for (int i = tid; i < n16; i += T) dst[i] = __ldg(src + i);
         }
-        const double *rs = reinterpret_cast<const double *>(smem + L.rs);
-        const double *Yl = reinterpret_cast<const double *>(smem + L.Yl);
-        const uint8_t *sideR = smem + L.sideR;
-        const uint8_t *sideC = smem + L.sideC;
-        const uint16_t *rowid = reinterpret_cast<const uint16_t *>(smem + L.rowid);
-        const uint16_t *colid = reinterpret_cast<const uint16_t *>(smem + L.colid);
-        const uint32_t *startR = reinterpret_cast<const uint32_t *>(smem + L.startR);
-        const uint32_t *startC = reinterpret_cast<const uint32_t *>(smem + L.startC);
-        double *theta = reinterpret_cast<double *>(smem + L.copy_bytes);   // M + 1, theta[M] = 0 (padding target)
+        const double *rs = reinterpret_cast<const double *>(simg + L.rs);
+        const double *Yl = reinterpret_cast<const double *>(simg + L.Yl);
+        const uint8_t *sideR = simg + L.sideR;
+        const uint8_t *sideC = simg + L.sideC;
+        const uint16_t *rowid = reinterpret_cast<const uint16_t *>(simg + L.rowid);
+        const uint16_t *colid = reinterpret_cast<const uint16_t *>(simg + L.colid);
+        const uint32_t *startR = reinterpret_cast<const uint32_t *>(simg + L.startR);
+        const uint32_t *startC = reinterpret_cast<const uint32_t *>(simg + L.startC);
+        double *theta = reinterpret_cast<double *>(smem);                   // M + 1, theta[M] = 0 (padding target)
         double *ratio = theta + (M + 1);                                    // NL + 1, ratio[NL] = 0
         for (int i = tid; i < M; i += T) theta[i] = 1.0;                    // src/em.cpp:20-21
         if (tid == 0) {
@@ -112,11 +135,11 @@ em_sell_kernel(const int32_t *__restrict__ queue, const int *__restrict__ qcount
                 double a1 = 0.0, a2 = 0.0;
                 int cnt = 0;
                 if (nP == 0) {
-                    line_sums<0>(sideC, startC[sl], startC[sl + 1], lane, theta, a1, a2, cnt);
+                    line_sums<0>(sideC, startC[sl], startC[sl + 1], lane, vec, a1, a2, cnt);
                 } else {
                     // dense semantics: a row with non-finite theta poisons every column it has a
                     // structural zero in (0*NaN), SURVEY Appendix C.14
-                    line_sums<1>(sideC, startC[sl], startC[sl + 1], lane, theta, a1, a2, cnt);
+                    line_sums<1>(sideC, startC[sl], startC[sl + 1], lane, vec, a1, a2, cnt);
                     if (cnt < nP) a1 = qnan();
                 }
                 if (j < NL) {
@@ -137,43 +160,45 @@ em_sell_kernel(const int32_t *__restrict__ queue, const int *__restrict__ qcount
                 const uint8_t *p = sideR + (size_t)kSlotBytes * startR[sl];
                 const uint32_t ns = startR[sl + 1] - startR[sl];
                 if (!hazard) {
-#pragma unroll 2
+#pragma unroll kSlotUnroll
                     for (uint32_t s = 0; s < ns; ++s, p += kSlotBytes) {
-                        const double ve = reinterpret_cast<const double *>(p)[lane];
-                        const double vo = reinterpret_cast<const double *>(p + 256)[lane];
-                        const uint32_t ie = reinterpret_cast<const uint16_t *>(p + 512)[lane];
-                        const uint32_t io = reinterpret_cast<const uint16_t *>(p + 576)[lane];
-                        a1 = __dadd_rn(a1, __dmul_rn(__dmul_rn(ve, th), ratio[ie]));
-                        a2 = __dadd_rn(a2, __dmul_rn(__dmul_rn(vo, th), ratio[io]));
+                        const double2 v = reinterpret_cast<const double2 *>(p)[lane];
+                        const uint32_t oe = reinterpret_cast<const uint16_t *>(p + 512)[lane];
+                        const uint32_t oo = reinterpret_cast<const uint16_t *>(p + 576)[lane];
+                        a1 = __dadd_rn(a1, __dmul_rn(__dmul_rn(v.x, th), vec_at(vec, oe)));
+                        a2 = __dadd_rn(a2, __dmul_rn(__dmul_rn(v.y, th), vec_at(vec, oo)));
                     }
                 } else {
                     for (uint32_t s = 0; s < ns; ++s, p += kSlotBytes) {
-                        const double ve = reinterpret_cast<const double *>(p)[lane];
-                        const double vo = reinterpret_cast<const double *>(p + 256)[lane];
-                        const uint32_t ie = reinterpret_cast<const uint16_t *>(p + 512)[lane];
-                        const uint32_t io = reinterpret_cast<const uint16_t *>(p + 576)[lane];
-                        double te = __dmul_rn(__dmul_rn(ve, th), ratio[ie]);
-                        double to = __dmul_rn(__dmul_rn(vo, th), ratio[io]);
+                        const double2 v = reinterpret_cast<const double2 *>(p)[lane];
+                        const uint32_t oe = reinterpret_cast<const uint16_t *>(p + 512)[lane];
+                        const uint32_t oo = reinterpret_cast<const uint16_t *>(p + 576)[lane];
+                        double te = __dmul_rn(__dmul_rn(v.x, th), vec_at(vec, oe));
+                        double to = __dmul_rn(__dmul_rn(v.y, th), vec_at(vec, oo));
                         if (te != te) te = 0.0;   // replace(nan, 0)  (:49)
                         if (to != to) to = 0.0;
                         a1 = __dadd_rn(a1, te);
                         a2 = __dadd_rn(a2, to);
                     }
                 }
+                // delta = max over {after > minvalue} of |after-before|/after  (:54-63); only
+                // "delta > conv" is needed: screen without the division.  The exact division is
+                // needed only inside the 2^-40 band around conv; it sits behind a warp-uniform
+                // branch (vote) so that the compiler cannot evaluate it speculatively.
+                bool inband = false;
+                double after = 0.0, diff = 0.0;
                 if (i < M) {
-                    const double after = __ddiv_rn(__dadd_rn(a1, a2), rs[i]);
+                    after = __ddiv_rn(__dadd_rn(a1, a2), rs[i]);
                     theta[i] = after;
                     if (!is_finite(after)) atomicAdd(&s_nf[par], 1);
-                    // delta = max over {after > minvalue} of |after-before|/after  (:54-63); only
-                    // "delta > conv" is needed: screen without the division, divide only inside
-                    // the 2^-40 band around conv
                     if (after > P.minvalue) {
-                        const double diff = fabs(__dadd_rn(after, -th));
+                        diff = fabs(__dadd_rn(after, -th));
                         if (diff > __dmul_rn(after, P.conv_hi)) flag = 1;
-                        else if (diff >= __dmul_rn(after, P.conv_lo)) {
-                            if (__ddiv_rn(diff, after) > P.conv) flag = 1;
-                        }
+                        else inband = (diff >= __dmul_rn(after, P.conv_lo));
                     }
+                }
+                if (BAMBU_V_LAZY ? __any_sync(0xffffffffu, inband) : inband) {
+                    if (inband && __ddiv_rn(diff, after) > P.conv) flag = 1;
                 }
             }
             over = __syncthreads_or(flag) != 0;
@@ -184,11 +209,12 @@ em_sell_kernel(const int32_t *__restrict__ queue, const int *__restrict__ qcount
         const double *KY = reinterpret_cast<const double *>(gimg + L.KY);
         const uint8_t *cm = gimg + L.cm;
         const uint8_t *eq = gimg + L.eq;
+        const uint32_t ratio_off = 8u * (uint32_t)(M + 1);
         for (int sl = warp; sl < nSliceC; sl += NW) {
             const int j = colid[sl * 32 + lane];
             double a1 = 0.0, a2 = 0.0;
             int cnt = 0;
-            line_sums<1>(sideC, startC[sl], startC[sl + 1], lane, theta, a1, a2, cnt);
+            line_sums<1>(sideC, startC[sl], startC[sl + 1], lane, vec, a1, a2, cnt);
             if (j < NL) {
                 double c = __dadd_rn(a1, a2);
                 if (cnt < nP) c = qnan();
@@ -209,11 +235,12 @@ em_sell_kernel(const int32_t *__restrict__ queue, const int *__restrict__ qcount
             const uint32_t s0 = startR[sl], s1 = startR[sl + 1];
             const uint8_t *p = sideR + (size_t)kSlotBytes * s0;
             for (uint32_t s = s0; s < s1; ++s, p += kSlotBytes) {
-                const double ve = reinterpret_cast<const double *>(p)[lane];
-                const double vo = reinterpret_cast<const double *>(p + 256)[lane];
-                const uint32_t ie = reinterpret_cast<const uint16_t *>(p + 512)[lane];
-                const uint32_t io = reinterpret_cast<const uint16_t *>(p + 576)[lane];
-                const double be = ratio[ie], bo = ratio[io];
+                const double2 v2 = reinterpret_cast<const double2 *>(p)[lane];
+                const double ve = v2.x, vo = v2.y;
+                const uint32_t oe = reinterpret_cast<const uint16_t *>(p + 512)[lane];
+                const uint32_t oo = reinterpret_cast<const uint16_t *>(p + 576)[lane];
+                const uint32_t ie = (oe - ratio_off) >> 3, io = (oo - ratio_off) >> 3;   // live column index
+                const double be = vec_at(vec, oe), bo = vec_at(vec, oo);
                 const double fe = __ldg(eq + (size_t)64 * s + lane) ? ve : __dmul_rn(ve, 0.0);        // fullAval = aval*equal
                 const double fo = __ldg(eq + (size_t)64 * s + 32 + lane) ? vo : __dmul_rn(vo, 0.0);
                 const double ue = __ldg(cm + ie) ? __dmul_rn(ve, 0.0) : ve;                            // uniqueAval = aval*!multi

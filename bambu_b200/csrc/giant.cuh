@@ -304,17 +304,23 @@ em_giant_kernel(const GiantDesc *__restrict__ descs, int n_giant, const uint8_t 
             grid.sync();
             // update: every CTA forms the whole theta' and the stopping test (src/em.cpp:50-63)
             int flag = (P.conv < 0.0) ? 1 : 0, nf = 0;
-            for (int i = tid; i < M; i += T) {
-                const double th = theta[i];
-                const double after = __ddiv_rn(__dadd_rn(__ldcg(S + 2 * i), __ldcg(S + 2 * i + 1)), rs[i]);
-                theta[i] = after;
-                nf += !is_finite(after);
-                if (after > P.minvalue) {
-                    const double diff = fabs(__dadd_rn(after, -th));
-                    if (diff > __dmul_rn(after, P.conv_hi)) flag = 1;
-                    else if (diff >= __dmul_rn(after, P.conv_lo)) {
-                        if (__ddiv_rn(diff, after) > P.conv) flag = 1;
+            for (int ib = 0; ib < M; ib += T) {      // uniform trip count: the band test votes per warp
+                const int i = ib + tid;
+                bool inband = false;
+                double after = 0.0, diff = 0.0;
+                if (i < M) {
+                    const double th = theta[i];
+                    after = __ddiv_rn(__dadd_rn(__ldcg(S + 2 * i), __ldcg(S + 2 * i + 1)), rs[i]);
+                    theta[i] = after;
+                    nf += !is_finite(after);
+                    if (after > P.minvalue) {
+                        diff = fabs(__dadd_rn(after, -th));
+                        if (diff > __dmul_rn(after, P.conv_hi)) flag = 1;
+                        else inband = (diff >= __dmul_rn(after, P.conv_lo));
                     }
+                }
+                if (__any_sync(0xffffffffu, inband)) {
+                    if (inband && __ddiv_rn(diff, after) > P.conv) flag = 1;
                 }
             }
             // block-wide: any flag, total non-finite count (identical in every CTA)

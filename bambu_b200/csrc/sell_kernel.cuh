@@ -59,12 +59,15 @@ __device__ __forceinline__ void sell_measure(SellSide &S, const uint16_t *__rest
     __syncthreads();
 }
 
-// write one side's slots.  dummy = index of the always-zero element of the vector this
-// side gathers from.  eq_out/eq_in: per-entry "equal" flags (row side only).
+// write one side's slots.  Slot = { (valE, valO) x 32 lanes | offE u16 x 32 | offO u16 x 32 };
+// an index is stored as the BYTE OFFSET of the gathered element inside the EM kernel's vector
+// region (theta at 0, ratio behind it): off = vec_off + 8 * index.  dummy = offset of the
+// always-zero element of the vector this side gathers from.  eq_out/eq_in: per-entry "equal"
+// flags (row side only).
 template <int T>
 __device__ __forceinline__ void sell_fill(const SellSide &S, const uint16_t *__restrict__ ptr,
                                           const uint16_t *__restrict__ idx, const double *__restrict__ val,
-                                          uint8_t *__restrict__ side, uint16_t dummy,
+                                          uint8_t *__restrict__ side, uint32_t vec_off, uint16_t dummy,
                                           const uint8_t *__restrict__ eq_in, uint8_t *__restrict__ eq_out)
 {
     const int tid = threadIdx.x;
@@ -77,16 +80,17 @@ __device__ __forceinline__ void sell_fill(const SellSide &S, const uint16_t *__r
             for (int k = ptr[i]; k < ptr[i + 1]; ++k) {
                 const uint16_t ix = idx[k];
                 const double v = val[k];
+                const uint16_t off = (uint16_t)(vec_off + 8u * (uint32_t)(ix >> 1));
                 if (ix & 1) {
                     uint8_t *slot = base + (size_t)kSlotBytes * ko;
-                    reinterpret_cast<double *>(slot + 256)[lane] = v;
-                    reinterpret_cast<uint16_t *>(slot + 576)[lane] = ix >> 1;
+                    reinterpret_cast<double *>(slot)[2 * lane + 1] = v;
+                    reinterpret_cast<uint16_t *>(slot + 576)[lane] = off;
                     if (eq_out) eq_out[(size_t)64 * (s0 + ko) + 32 + lane] = eq_in[k];
                     ++ko;
                 } else {
                     uint8_t *slot = base + (size_t)kSlotBytes * ke;
-                    reinterpret_cast<double *>(slot)[lane] = v;
-                    reinterpret_cast<uint16_t *>(slot + 512)[lane] = ix >> 1;
+                    reinterpret_cast<double *>(slot)[2 * lane] = v;
+                    reinterpret_cast<uint16_t *>(slot + 512)[lane] = off;
                     if (eq_out) eq_out[(size_t)64 * (s0 + ke) + lane] = eq_in[k];
                     ++ke;
                 }
@@ -94,13 +98,13 @@ __device__ __forceinline__ void sell_fill(const SellSide &S, const uint16_t *__r
         }
         for (; ke < Ls; ++ke) {
             uint8_t *slot = base + (size_t)kSlotBytes * ke;
-            reinterpret_cast<double *>(slot)[lane] = 0.0;
+            reinterpret_cast<double *>(slot)[2 * lane] = 0.0;
             reinterpret_cast<uint16_t *>(slot + 512)[lane] = dummy;
             if (eq_out) eq_out[(size_t)64 * (s0 + ke) + lane] = 0;
         }
         for (; ko < Ls; ++ko) {
             uint8_t *slot = base + (size_t)kSlotBytes * ko;
-            reinterpret_cast<double *>(slot + 256)[lane] = 0.0;
+            reinterpret_cast<double *>(slot)[2 * lane + 1] = 0.0;
             reinterpret_cast<uint16_t *>(slot + 576)[lane] = dummy;
             if (eq_out) eq_out[(size_t)64 * (s0 + ko) + 32 + lane] = 0;
         }
@@ -191,9 +195,12 @@ sell_kernel(const int32_t *__restrict__ work, int n_work, const int64_t *__restr
         for (int w = tid; w <= R.nSlice; w += T) startR[w] = R.start[w];
         for (int w = tid; w <= C.nSlice; w += T) startC[w] = C.start[w];
     }
-    // row side gathers ratio[] (dummy element NL), column side gathers theta[] (dummy element M)
-    sell_fill<T>(R, rp, cidx, cval, img + L.sideR, (uint16_t)NL, img1 + L1.eq, img + L.eq);
-    sell_fill<T>(C, cp, ridx, rval, img + L.sideC, (uint16_t)M, nullptr, nullptr);
+    // vector region of the EM kernel: theta[M+1] at byte 0, ratio[NL+1] behind it.  The row side
+    // gathers ratio[] (dummy element NL), the column side gathers theta[] (dummy element M).
+    const uint32_t ratio_off = 8u * (uint32_t)(M + 1);
+    sell_fill<T>(R, rp, cidx, cval, img + L.sideR, ratio_off, (uint16_t)(ratio_off + 8u * (uint32_t)NL), img1 + L1.eq,
+                 img + L.eq);
+    sell_fill<T>(C, cp, ridx, rval, img + L.sideC, 0u, (uint16_t)(8u * (uint32_t)M), nullptr, nullptr);
 
     if (tid == 0) {
         GroupImg gi;
