@@ -119,7 +119,7 @@ struct Ctrl {   // device control block, zeroed at the start of every run
     unsigned long long pool_ctr;
     int qcount[8];
     int ticket[8];
-    unsigned int gflags[8];   // streamed tier: hazard flags, inf-column count, non-finite flag
+    unsigned int gflags[128]; // streamed tier: [0..7] hazard / stopping flags, [64..65] grid barrier (own cache line)
 };
 
 // ------------------------------------------------------------------------------
@@ -455,7 +455,7 @@ static int slot_prepare(Slot &s, const int64_t *grp_row_ptr, const int64_t *grp_
         const double ub = 20.0 * (double)e + 18.0 * (double)(M + N) + 64.0;
         if (M > kMaxIndex || N > kMaxIndex || M + N > kMaxVecElems || ub > (double)kSmemMax || forced_giant) {
             // streamed tier: image in global memory, all SMs iterate on this one group
-            if (8 * M > (int64_t)kSmemMax || M > INT32_MAX / 8 || N > INT32_MAX / 2 || e > (int64_t)UINT32_MAX - 64)
+            if (8 * (M + 1) + 16 + 512 * (kGiantThreads / 32) > (int64_t)kSmemMax || M > INT32_MAX / 8 || N > INT32_MAX / 2 || e > (int64_t)UINT32_MAX - 64)
                 return fail(BAMBU_EM_EINVAL, "group %lld (M=%lld N=%lld entries=%lld) exceeds the streamed tier",
                             (long long)g, (long long)M, (long long)N, (long long)e);
             GiantDesc d;
@@ -465,7 +465,7 @@ static int slot_prepare(Slot &s, const int64_t *grp_row_ptr, const int64_t *grp_
             d.base = goff;
             goff += d.total;
             giants.push_back(d);
-            gsmem = std::max<uint32_t>(gsmem, (uint32_t)(8 * M));
+            gsmem = std::max<uint32_t>(gsmem, (uint32_t)(8 * (M + 1) + 16 + 512 * (kGiantThreads / 32)));
             continue;
         }
         const uint32_t bytes = em_smem_bytes((uint32_t)M, (uint32_t)N, (uint32_t)e);

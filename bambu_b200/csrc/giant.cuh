@@ -37,6 +37,9 @@ struct GiantDesc {
     int64_t base;         // image base inside the giant buffer
     // sections (relative to base)
     int64_t rs, Yl, KY, cm, hp, cidx, cval, eq, cp, ridx, rval;
+    // column side in SELL order (slot-major inside slices of 32 length-sorted columns): E-phase reads are coalesced
+    int64_t ccol, cstart, sval, sidx;
+    int32_t nSliceC, slotsC;
     // scratch for packing / iterating
     int64_t colmap, colcnt, cursor, hcnt, ratio, S, cntS;
     int64_t total;
@@ -57,6 +60,14 @@ __host__ inline void giant_layout(GiantDesc &d, int64_t M, int64_t N, int64_t e)
     d.cp = o; o = al(o + 4 * (N + 1));
     d.ridx = o; o = al(o + 4 * e);
     d.rval = o; o = al(o + 8 * e);
+    {
+        const int64_t nsl = (N + 31) / 32;
+        const int64_t slots_ub = e / 32 + M + nsl + 2;      // sum of slice maxima of length-sorted columns
+        d.ccol = o; o = al(o + 4 * 32 * nsl);
+        d.cstart = o; o = al(o + 4 * (nsl + 1));
+        d.sval = o; o = al(o + 8 * 32 * slots_ub);
+        d.sidx = o; o = al(o + 4 * 32 * slots_ub);
+    }
     d.colmap = o; o = al(o + 4 * N);
     d.colcnt = o; o = al(o + 4 * (N + 1));
     d.cursor = o; o = al(o + 4 * N);
@@ -196,6 +207,56 @@ pack_giant_kernel(ArenaDev A, GiantDesc *__restrict__ descs, int n_giant, uint8_
             rval[q] = kv;
         }
     }
+    __syncthreads();
+    // F: column side in SELL order.  colmap/colcnt/cursor are free now: reuse them as
+    //    len[NL] (colmap), histogram (shared), position -> column (ccol)
+    {
+        __shared__ uint32_t hist[1024];
+        uint32_t *ccol = reinterpret_cast<uint32_t *>(img + D.ccol);
+        uint32_t *cstart = reinterpret_cast<uint32_t *>(img + D.cstart);
+        double *sval = reinterpret_cast<double *>(img + D.sval);
+        uint32_t *sidx = reinterpret_cast<uint32_t *>(img + D.sidx);
+        const int nsl = ((int)NL + 31) / 32;
+        for (int b = tid; b < 1024; b += T) hist[b] = 0;
+        __syncthreads();
+        for (int j = tid; j < (int)NL; j += T) atomicAdd(&hist[1023 - min(cp[j + 1] - cp[j], 1023u)], 1u);
+        __syncthreads();
+        block_excl_scan<T>(hist, 1024, s_warp);
+        for (int j = tid; j < (int)NL; j += T) {
+            const uint32_t pos = atomicAdd(&hist[1023 - min(cp[j + 1] - cp[j], 1023u)], 1u);
+            ccol[pos] = (uint32_t)j;
+        }
+        for (int p = (int)NL + tid; p < nsl * 32; p += T) ccol[p] = NL;
+        __syncthreads();
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int w = warp; w < nsl; w += T / 32) {
+            const uint32_t j = ccol[w * 32 + lane];
+            uint32_t L = (j < NL) ? cp[j + 1] - cp[j] : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) L = max(L, __shfl_xor_sync(0xffffffffu, L, o));
+            if (lane == 0) cstart[w] = L;
+        }
+        __syncthreads();
+        const uint32_t slots = block_excl_scan<T>(cstart, nsl, s_warp);
+        if (tid == 0) { cstart[nsl] = slots; D.nSliceC = nsl; D.slotsC = (int32_t)slots; }
+        __syncthreads();
+        for (int p = tid; p < nsl * 32; p += T) {
+            const uint32_t j = ccol[p];
+            const int ln = p & 31, w = p >> 5;
+            const uint32_t s0 = cstart[w], Ls = cstart[w + 1] - s0;
+            uint32_t k = 0;
+            if (j < NL) {
+                for (uint32_t q = cp[j]; q < cp[j + 1]; ++q, ++k) {
+                    sval[(size_t)(s0 + k) * 32 + ln] = rval[q];
+                    sidx[(size_t)(s0 + k) * 32 + ln] = ridx[q];
+                }
+            }
+            for (; k < Ls; ++k) {     // padding: value 0 times theta[M] = 0
+                sval[(size_t)(s0 + k) * 32 + ln] = 0.0;
+                sidx[(size_t)(s0 + k) * 32 + ln] = ((uint32_t)M << 1);
+            }
+        }
+    }
     if (tid == 0) {
         D.NL = (int32_t)NL;
         D.nnzL = (int32_t)nnzL;
@@ -203,31 +264,92 @@ pack_giant_kernel(ArenaDev A, GiantDesc *__restrict__ descs, int n_giant, uint8_
     }
 }
 
-// ---- EM ------------------------------------------------------------------------------------
-// ordered sum of one stream [lo, hi): 32 products at a time, added in stream order.
-// NSUM = 1: sum of (v*th)*x ; NSUM = 3: also the full-length and unique variants (epilogue).
-template <bool HAZARD>
-__device__ __forceinline__ double stream_sum(const uint32_t *__restrict__ cidx, const double *__restrict__ cval,
-                                             uint32_t lo, uint32_t hi, int lane, double th,
-                                             const double *ratio)
+// ---- grid-wide barrier (cooperative launch => every CTA is resident) -------------------------
+// bar[0] = arrival counter, bar[1] = generation.  One atomic per CTA, the last arrival opens the
+// next generation; the others spin on it.  Cheaper than cg::grid_group::sync() (no L1 flush).
+__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int n_ctas)
 {
-    double acc = 0.0;
-    for (uint32_t base = lo; base < hi; base += 32) {
-        const uint32_t k = base + lane;
-        double t = 0.0;
-        if (k < hi) {
-            t = __dmul_rn(__dmul_rn(cval[k], th), __ldcg(ratio + cidx[k]));
-            if (HAZARD && t != t) t = 0.0;   // replace(nan, 0)  (src/em.cpp:49)
-        }
-        const int n = min(32u, hi - base);
-        if (n == 32) {
-#pragma unroll
-            for (int q = 0; q < 32; ++q) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, t, q));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned int *gen = bar + 1;
+        const unsigned int my_gen = *gen;
+        __threadfence();                                   // this CTA's writes before the arrival
+        if (atomicAdd(bar, 1u) == n_ctas - 1) {
+            bar[0] = 0;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);                        // release
         } else {
-            for (int q = 0; q < n; ++q) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, t, q));
+            while (*gen == my_gen) { __nanosleep(32); }
         }
+        __threadfence();                                   // acquire
     }
-    return acc;
+    __syncthreads();
+}
+
+// ---- EM ------------------------------------------------------------------------------------
+// Ordered sums of the two streams of one row (even columns: [loA, hiA), odd columns: [loB, hiB)) by
+// one warp: 32 products of each stream at a time, then 32 steps that add product q of either stream
+// to its accumulator -- two independent add chains, every lane holding the same accumulators.
+// Software pipeline (the SM issues in order, so a load must be issued well before its first use;
+// L2 latency under this load is several hundred cycles, one batch's add chain ~300): batch b+3
+// loads its values and column indices, batch b+2 gathers its ratios, batch b is multiplied and added.
+template <bool HAZARD>
+__device__ __forceinline__ void row_streams(const uint32_t *__restrict__ cidx, const double *__restrict__ cval,
+                                            uint32_t loA, uint32_t hiA, uint32_t loB, uint32_t hiB, int lane, double th,
+                                            const double *ratio, double *stage /* 64 doubles of this warp */,
+                                            double &sA, double &sB)
+{
+    const uint32_t nA = hiA - loA, nB = hiB - loB, nmax = max(nA, nB);
+    double acc = 0.0;     // lane 0: even-column stream, lane 1: odd-column stream
+    // stage 1 of batches 0 and 1, stage 2 of batch 0
+    auto ld_v = [&](uint32_t lo, uint32_t hi, uint32_t base) { const uint32_t k = lo + base + lane; return (k < hi) ? cval[k] : 0.0; };
+    auto ld_c = [&](uint32_t lo, uint32_t hi, uint32_t base) { const uint32_t k = lo + base + lane; return (k < hi) ? cidx[k] : 0xffffffffu; };
+    auto ld_r = [&](uint32_t c) { return (c != 0xffffffffu) ? __ldcg(ratio + c) : 0.0; };
+    // values / column indices are loaded three batches ahead, ratios gathered two batches ahead
+    double vA0 = ld_v(loA, hiA, 0), vB0 = ld_v(loB, hiB, 0);
+    uint32_t cA0 = ld_c(loA, hiA, 0), cB0 = ld_c(loB, hiB, 0);
+    double vA1 = ld_v(loA, hiA, 32), vB1 = ld_v(loB, hiB, 32);
+    uint32_t cA1 = ld_c(loA, hiA, 32), cB1 = ld_c(loB, hiB, 32);
+    double vA2 = ld_v(loA, hiA, 64), vB2 = ld_v(loB, hiB, 64);
+    uint32_t cA2 = ld_c(loA, hiA, 64), cB2 = ld_c(loB, hiB, 64);
+    double rA0 = ld_r(cA0), rB0 = ld_r(cB0);
+    double rA1 = ld_r(cA1), rB1 = ld_r(cB1);
+    for (uint32_t base = 0; base < nmax; base += 32) {
+        const double vA3 = ld_v(loA, hiA, base + 96), vB3 = ld_v(loB, hiB, base + 96);
+        const uint32_t cA3 = ld_c(loA, hiA, base + 96), cB3 = ld_c(loB, hiB, base + 96);
+        const double rA2 = ld_r(cA2), rB2 = ld_r(cB2);
+        // stage 3: products of batch b, then the ordered adds
+        double tA = __dmul_rn(__dmul_rn(vA0, th), rA0), tB = __dmul_rn(__dmul_rn(vB0, th), rB0);
+        if (HAZARD) {
+            if (tA != tA) tA = 0.0;   // replace(nan, 0)  (src/em.cpp:49)
+            if (tB != tB) tB = 0.0;
+        }
+        const int qa = (int)min(32u, nA - min(nA, base)), qb = (int)min(32u, nB - min(nB, base));
+        // the 2 x 32 products go through shared memory; lanes 0 and 1 add their stream's in order
+        // (a shuffle per step would make the SM's shuffle unit the bottleneck)
+        stage[lane] = tA;
+        stage[32 + lane] = tB;
+        __syncwarp();
+        if (lane < 2) {
+            const double *src = stage + 32 * lane;
+            const int n = lane ? qb : qa;
+            if (n == 32) {
+#pragma unroll
+                for (int q = 0; q < 32; q += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(src + q);
+                    acc = __dadd_rn(__dadd_rn(acc, v.x), v.y);
+                }
+            } else {
+                for (int q = 0; q < n; ++q) acc = __dadd_rn(acc, src[q]);
+            }
+        }
+        __syncwarp();
+        vA0 = vA1; vB0 = vB1; rA0 = rA1; rB0 = rB1;
+        vA1 = vA2; vB1 = vB2; rA1 = rA2; rB1 = rB2;
+        vA2 = vA3; vB2 = vB3; cA2 = cA3; cB2 = cB3;
+    }
+    sA = __shfl_sync(0xffffffffu, acc, 0);
+    sB = __shfl_sync(0xffffffffu, acc, 1);
 }
 
 template <int T>
@@ -237,11 +359,16 @@ em_giant_kernel(const GiantDesc *__restrict__ descs, int n_giant, const uint8_t 
                 int32_t *__restrict__ iters, int32_t *__restrict__ status, unsigned int *gflags /* 8 words, zeroed */)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    cg::grid_group grid = cg::this_grid();
+    unsigned int *bar = gflags + 64;  // arrival counter + generation, on a cache line of their own
+                                      // (148 CTAs poll it; the stopping flags must not share the line)
+    const unsigned int n_ctas = gridDim.x;
     double *theta = reinterpret_cast<double *>(smem);   // M, private copy per CTA
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t gtid = (int64_t)blockIdx.x * T + tid, gthreads = (int64_t)gridDim.x * T;
-    const int64_t gwarp = gtid >> 5, gwarps = gthreads >> 5;
+    // warp tasks are dealt round-robin over the CTAs (task w -> CTA w % n, warp w / n): a phase with
+    // fewer tasks than warps then keeps every SM lightly and evenly loaded
+    const int64_t gwarps = gthreads >> 5;
+    const int64_t gwarp = (int64_t)(tid >> 5) * gridDim.x + blockIdx.x;
     (void)gbuf_c;
 
     for (int gi = 0; gi < n_giant; ++gi) {
@@ -259,82 +386,110 @@ em_giant_kernel(const GiantDesc *__restrict__ descs, int n_giant, const uint8_t 
         const uint32_t *cp = reinterpret_cast<const uint32_t *>(img + D.cp);
         const uint32_t *ridx = reinterpret_cast<const uint32_t *>(img + D.ridx);
         const double *rval = reinterpret_cast<const double *>(img + D.rval);
+        const uint32_t *ccol = reinterpret_cast<const uint32_t *>(img + D.ccol);
+        const uint32_t *cstart = reinterpret_cast<const uint32_t *>(img + D.cstart);
+        const double *sval = reinterpret_cast<const double *>(img + D.sval);
+        const uint32_t *sidx = reinterpret_cast<const uint32_t *>(img + D.sidx);
+        const int nSliceC = D.nSliceC;
         double *ratio = reinterpret_cast<double *>(img + D.ratio);
-        double *S = reinterpret_cast<double *>(img + D.S);
+        double *S = reinterpret_cast<double *>(img + D.S);          // [0, M): theta of the current update; then sums
         uint32_t *cntS = reinterpret_cast<uint32_t *>(img + D.cntS);
-        unsigned int *hz = gflags;        // [0..1] hazard flags by update parity, [2] Q
+        // [0..1] hazard by update parity, [2] inf-column count, [3] non-finite estimate,
+        // [4..5] "delta > conv" by update parity, [6..7] non-finite theta count by update parity
+        unsigned int *hz = gflags;
         const int64_t row0 = grp_row_ptr[D.g];
+        // per-warp staging of 2 x 32 products behind theta[M+1]
+        double *stage = reinterpret_cast<double *>(smem + align_up(8u * (uint32_t)(M + 1), 16)) + 64 * (tid >> 5);
 
         for (int i = tid; i < M; i += T) theta[i] = 1.0;   // src/em.cpp:20-21
-        if (gtid == 0) { hz[0] = hz[1] = 0; hz[2] = 0; }
-        int nP = 0;                                          // non-finite thetas (same value in every CTA)
+        if (tid == 0) theta[M] = 0.0;                       // padding entries of the column SELL point here
+        if (gtid == 0) { for (int q = 0; q < 8; ++q) if (q != 3) hz[q] = 0; }
+        int nP = 0;                                          // non-finite thetas entering the update
         int iter = 0;
         bool over = (1.0 > P.conv);
-        grid.sync();
+        grid_barrier(bar, n_ctas);
         while (over && iter < P.maxiter - 1) {
             ++iter;
             const int par = iter & 1;
             // E-phase: c_j = sum_i a_ij*theta_i, ratio_j = Y_j / c_j   (src/em.cpp:46-48)
-            for (int64_t j = gtid; j < NL; j += gthreads) {
+            // one lane per live column, a warp per slice of 32 length-sorted columns; slot-major storage
+            // makes every load a coalesced 256 B / 128 B line
+            for (int64_t w = gwarp; w < nSliceC; w += gwarps) {
+                const uint32_t j = ccol[w * 32 + lane];
+                const uint32_t s0 = cstart[w], s1 = cstart[w + 1];
                 double a1 = 0.0, a2 = 0.0;
                 int cnt = 0;
-                for (uint32_t k = cp[j]; k < cp[j + 1]; ++k) {
-                    const uint32_t ri = ridx[k];
-                    const double th = theta[ri >> 1];
-                    const double t = __dmul_rn(rval[k], th);
-                    if (nP) cnt += !is_finite(th);
-                    if (ri & 1u) a2 = __dadd_rn(a2, t); else a1 = __dadd_rn(a1, t);
-                }
-                if (cnt < nP) a1 = qnan();   // dense 0*NaN at this column's structural zeros (Appendix C.14)
-                const double r = __ddiv_rn(Yl[j], __dadd_rn(a1, a2));
-                ratio[j] = r;
-                if (!is_finite(r)) atomicOr(&hz[par], 1u);
-            }
-            grid.sync();
-            // M-phase: one warp per half-row, ordered chain  (src/em.cpp:48-50)
-            const bool hazard = (__ldcg(&hz[par]) != 0) || (nP != 0);
-            if (gtid == 0) hz[par ^ 1] = 0;
-            for (int64_t task = gwarp; task < 2 * (int64_t)M; task += gwarps) {
-                const double th = theta[task >> 1];
-                const uint32_t lo = hp[task], hi = hp[task + 1];
-                const double s = hazard ? stream_sum<true>(cidx, cval, lo, hi, lane, th, ratio)
-                                        : stream_sum<false>(cidx, cval, lo, hi, lane, th, ratio);
-                if (lane == 0) S[task] = s;
-            }
-            grid.sync();
-            // update: every CTA forms the whole theta' and the stopping test (src/em.cpp:50-63)
-            int flag = (P.conv < 0.0) ? 1 : 0, nf = 0;
-            for (int ib = 0; ib < M; ib += T) {      // uniform trip count: the band test votes per warp
-                const int i = ib + tid;
-                bool inband = false;
-                double after = 0.0, diff = 0.0;
-                if (i < M) {
-                    const double th = theta[i];
-                    after = __ddiv_rn(__dadd_rn(__ldcg(S + 2 * i), __ldcg(S + 2 * i + 1)), rs[i]);
-                    theta[i] = after;
-                    nf += !is_finite(after);
-                    if (after > P.minvalue) {
-                        diff = fabs(__dadd_rn(after, -th));
-                        if (diff > __dmul_rn(after, P.conv_hi)) flag = 1;
-                        else inband = (diff >= __dmul_rn(after, P.conv_lo));
+                for (uint32_t sb = s0; sb < s1; sb += 8) {            // 8 slots' loads in flight at a time
+                    uint32_t ri[8];
+                    double rv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const bool ok = (sb + u < s1);
+                        ri[u] = ok ? sidx[(size_t)(sb + u) * 32 + lane] : ((uint32_t)M << 1);
+                        rv[u] = ok ? sval[(size_t)(sb + u) * 32 + lane] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (sb + u < s1) {
+                            const double th = theta[ri[u] >> 1];
+                            const double t = __dmul_rn(rv[u], th);
+                            if (nP) cnt += !is_finite(th);
+                            if (ri[u] & 1u) a2 = __dadd_rn(a2, t); else a1 = __dadd_rn(a1, t);
+                        }
                     }
                 }
-                if (__any_sync(0xffffffffu, inband)) {
-                    if (inband && __ddiv_rn(diff, after) > P.conv) flag = 1;
+                if (j < (uint32_t)NL) {
+                    if (cnt < nP) a1 = qnan();   // dense 0*NaN at this column's structural zeros (Appendix C.14)
+                    const double r = __ddiv_rn(Yl[j], __dadd_rn(a1, a2));
+                    ratio[j] = r;
+                    if (!is_finite(r)) atomicOr(&hz[par], 1u);
                 }
             }
-            // block-wide: any flag, total non-finite count (identical in every CTA)
-            over = __syncthreads_or(flag) != 0;
-            {
-                __shared__ int s_nf;
-                if (tid == 0) s_nf = 0;
-                __syncthreads();
-                if (nf) atomicAdd(&s_nf, nf);
-                __syncthreads();
-                nP = s_nf;
-                __syncthreads();
+            grid_barrier(bar, n_ctas);
+            // M-phase: one warp per row, both parity streams in lockstep; the warp forms theta'_i and
+            // the row's share of the stopping test  (src/em.cpp:48-63)
+            const bool hazard = (__ldcg(&hz[par]) != 0) || (nP != 0);
+            // every CTA is past the barrier, so nobody still reads the other parity's flags
+            if (gtid == 0) { hz[par ^ 1] = 0; hz[4 + (par ^ 1)] = 0; hz[6 + (par ^ 1)] = 0; }
+            for (int64_t i = gwarp; i < M; i += gwarps) {
+                const double th = theta[i];
+                const uint32_t loA = hp[2 * i], hiA = hp[2 * i + 1], hiB = hp[2 * i + 2];
+                double sA, sB;
+                if (hazard) row_streams<true>(cidx, cval, loA, hiA, hiA, hiB, lane, th, ratio, stage, sA, sB);
+                else row_streams<false>(cidx, cval, loA, hiA, hiA, hiB, lane, th, ratio, stage, sA, sB);
+                const double after = __ddiv_rn(__dadd_rn(sA, sB), rs[i]);     // every lane: same value
+                bool inband = false;
+                double diff = 0.0;
+                int flag = (P.conv < 0.0) ? 1 : 0;
+                if (after > P.minvalue) {
+                    diff = fabs(__dadd_rn(after, -th));
+                    if (diff > __dmul_rn(after, P.conv_hi)) flag = 1;
+                    else inband = (diff >= __dmul_rn(after, P.conv_lo));
+                }
+                if (inband && __ddiv_rn(diff, after) > P.conv) flag = 1;   // warp-uniform: all lanes agree
+                if (lane == 0) {
+                    S[i] = after;
+                    if (flag) atomicOr(&hz[4 + par], 1u);
+                    if (!is_finite(after)) atomicAdd(&hz[6 + par], 1u);
+                }
             }
+            grid_barrier(bar, n_ctas);
+            // every CTA refreshes its private theta; the flags are the same for all
+            {
+                const unsigned int f_over = __ldcg(&hz[4 + par]);
+                for (int i0 = tid; i0 < M; i0 += 4 * T) {
+                    double v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) v[u] = (i0 + u * T < M) ? __ldcg(S + i0 + u * T) : 0.0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (i0 + u * T < M) theta[i0 + u * T] = v[u];
+                }
+                over = f_over != 0;
+            }
+            nP = (int)__ldcg(&hz[6 + par]);
+            __syncthreads();
         }
+        grid_barrier(bar, n_ctas);   // S is reused for the epilogue sums: nobody may still be reading theta from it
 
         // ---- epilogue: src/em.cpp:97-102 ----------------------------------------------------
         for (int64_t j = gtid; j < NL; j += gthreads) {
@@ -354,7 +509,7 @@ em_giant_kernel(const GiantDesc *__restrict__ descs, int n_giant, const uint8_t 
             ratio[j] = b;
             if (fabs(b) > 1.7976931348623157e308) atomicAdd(&hz[2], 1u);
         }
-        grid.sync();
+        grid_barrier(bar, n_ctas);
         for (int64_t task = gwarp; task < 2 * (int64_t)M; task += gwarps) {
             const double th = theta[task >> 1];
             const uint32_t lo = hp[task], hi = hp[task + 1];
@@ -388,7 +543,7 @@ em_giant_kernel(const GiantDesc *__restrict__ descs, int n_giant, const uint8_t 
                 cntS[task] = cnt;
             }
         }
-        grid.sync();
+        grid_barrier(bar, n_ctas);
         const unsigned int Q = __ldcg(&hz[2]);
         int bad = 0;
         for (int64_t i = gtid; i < M; i += gthreads) {
@@ -404,13 +559,13 @@ em_giant_kernel(const GiantDesc *__restrict__ descs, int n_giant, const uint8_t 
             bad |= !(is_finite(e0) && is_finite(e1) && is_finite(e2));
         }
         if (bad) atomicOr(&hz[3], 1u);
-        grid.sync();
+        grid_barrier(bar, n_ctas);
         if (gtid == 0) {
             iters[D.g] = iter;
             status[D.g] = ((iter >= P.maxiter - 1 && over) ? 1 : 0) | (__ldcg(&hz[3]) ? 2 : 0);
             hz[3] = 0;
         }
-        grid.sync();
+        grid_barrier(bar, n_ctas);
     }
 }
 
