@@ -39,6 +39,15 @@ SYMBOLS = {
                                                   ctypes.POINTER(ctypes.c_float)]),
     "bambu_em_plan_last_run_launches": (ctypes.c_int, [_p, ctypes.POINTER(_i32)]),
     "bambu_em_plan_device_bytes": (ctypes.c_int, [_p, ctypes.POINTER(_i64)]),
+    "bambu_quant_last_error": (ctypes.c_char_p, []),
+    "bambu_quant_pack_create": (ctypes.c_int, [ctypes.POINTER(_p), _i64, _p, _p, _p, _p, _p, _p, _p, _i32]),
+    "bambu_quant_pack_free": (ctypes.c_int, [_p]),
+    "bambu_quant_pack_sizes": (ctypes.c_int, [_p] + [ctypes.POINTER(_i64)] * 6 + [ctypes.POINTER(_f64)]),
+    "bambu_quant_pack_arena": (ctypes.c_int, [_p] + [ctypes.POINTER(_p)] * 10),
+    "bambu_quant_pack_bookkeeping": (ctypes.c_int, [_p] + [ctypes.POINTER(_p)] * 3),
+    "bambu_quant_merge": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, ctypes.POINTER(_i64)]),
+    "bambu_quantDT": (ctypes.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _f64, _f64, _p, _p, _p, _p,
+                                     ctypes.POINTER(_i64), ctypes.POINTER(_f64)]),
 }
 
 
@@ -72,4 +81,10 @@ def lib():
 
 def check(rc: int) -> None:
     if rc != 0:
-        raise BambuEmError(rc, lib().bambu_em_last_error().decode())
+        msg = lib().bambu_em_last_error().decode() or lib().bambu_quant_last_error().decode()
+        raise BambuEmError(rc, msg)
+
+
+def check_quant(rc: int) -> None:
+    if rc != 0:
+        raise BambuEmError(rc, lib().bambu_quant_last_error().decode() or lib().bambu_em_last_error().decode())

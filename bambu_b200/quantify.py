@@ -270,6 +270,101 @@ def pack_quantDT(readClassDt, emParameters=None) -> PackedQuant:
     return out
 
 
+def _gene_codes(gid):
+    """Any integer coding of GENEID (the native packer numbers genes by first appearance itself)."""
+    gid = np.asarray(gid)
+    if gid.dtype.kind in "iu":
+        return gid.astype(np.int64)
+    return np.unique(gid, return_inverse=True)[1].astype(np.int64)
+
+
+def pack_quantDT_native(readClassDt, emParameters=None) -> PackedQuant:
+    """The same as :func:`pack_quantDT`, done by the native packer of ``libbambu_em.so``
+    (``bambu_quant_pack_create``, csrc/quant_pack.cpp) -- radix sorts and linear passes instead of
+    numpy group-bys; ~40x faster on a 2M-row sample.  Identical output (tests/test_quant_pack.py)."""
+    import ctypes
+    from . import _lib
+    par = setEmParameters(emParameters)
+    if readClassDt is None:
+        raise ValueError("Input object is missing.")
+    if any(k not in readClassDt for k in ("GENEID", "txid", "eqClassId", "nobs")):
+        raise ValueError("Columns GENEID, txid, eqClassId, nobs, are missing from object.")
+    L = _lib.lib()
+    n = len(readClassDt["txid"])
+    c = lambda a, dt: np.ascontiguousarray(np.asarray(a), dtype=dt)      # noqa: E731
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else None   # noqa: E731
+    gene = _gene_codes(readClassDt["GENEID"])
+    tx, eq = c(readClassDt["txid"], np.int64), c(readClassDt["eqClassId"], np.int64)
+    nobs = c(readClassDt["nobs"], np.float64)
+    equal = c(np.asarray(readClassDt["equal"], dtype=bool), np.uint8) if "equal" in readClassDt else None
+    rcw = c(readClassDt["rcWidth"], np.float64) if "rcWidth" in readClassDt else None
+    txlen = c(readClassDt["txlen"], np.float64) if "txlen" in readClassDt else None
+    h = ctypes.c_void_p()
+    rc = L.bambu_quant_pack_create(ctypes.byref(h), n, ptr(gene), ptr(tx), ptr(eq), ptr(nobs), ptr(equal), ptr(rcw),
+                                   ptr(txlen), int(bool(par["degradationBias"])))
+    if rc:
+        raise ValueError(L.bambu_quant_last_error().decode())
+    try:
+        sz = [ctypes.c_int64() for _ in range(6)]
+        d = ctypes.c_double()
+        L.bambu_quant_pack_sizes(h, *[ctypes.byref(x) for x in sz], ctypes.byref(d))
+        ng, rows, cols, nnz, n_out, n_uo = (int(x.value) for x in sz)
+        ps = [ctypes.c_void_p() for _ in range(10)]
+        L.bambu_quant_pack_arena(h, *[ctypes.byref(x) for x in ps])
+
+        def arr(p, count, dt):
+            if count == 0:
+                return np.zeros(0, dt)
+            buf = (ctypes.c_char * (count * np.dtype(dt).itemsize)).from_address(p.value)
+            return np.frombuffer(buf, dtype=dt).copy()
+        out = PackedQuant()
+        out.arena = Arena(arr(ps[0], ng + 1, np.int64), arr(ps[1], ng + 1, np.int64), arr(ps[2], rows + 1, np.int64),
+                          arr(ps[3], nnz, np.int32), arr(ps[4], nnz, np.float64), arr(ps[5], nnz, np.uint8),
+                          arr(ps[6], cols, np.float64), arr(ps[7], cols, np.float64), arr(ps[8], cols, np.uint8),
+                          arr(ps[9], rows, np.int32))
+        bs = [ctypes.c_void_p() for _ in range(3)]
+        L.bambu_quant_pack_bookkeeping(h, *[ctypes.byref(x) for x in bs])
+        out.out_txid = arr(bs[0], n_out, np.int64)
+        out.unobserved_txid = arr(bs[1], n_uo, np.int64)
+        out.gene_grp_id = arr(bs[2], ng, np.int64)
+        out.d_rate = float(d.value)
+    finally:
+        L.bambu_quant_pack_free(h)
+    return out
+
+
+def bambu_quantDT_native(readClassDt, emParameters=None):
+    """``bambu.quantDT`` as ONE call into the library (``bambu_quantDT``: native pack -> CUDA EM ->
+    native merge).  Returns the same dict as :func:`bambu_quantDT` plus ``d_rate``."""
+    import ctypes
+    from . import _lib
+    par = setEmParameters(emParameters)
+    if readClassDt is None or any(k not in readClassDt for k in ("GENEID", "txid", "eqClassId", "nobs")):
+        raise ValueError("Columns GENEID, txid, eqClassId, nobs, are missing from object.")
+    L = _lib.lib()
+    n = len(readClassDt["txid"])
+    c = lambda a, dt: np.ascontiguousarray(np.asarray(a), dtype=dt)      # noqa: E731
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else None   # noqa: E731
+    gene = _gene_codes(readClassDt["GENEID"])
+    tx, eq = c(readClassDt["txid"], np.int64), c(readClassDt["eqClassId"], np.int64)
+    nobs = c(readClassDt["nobs"], np.float64)
+    equal = c(np.asarray(readClassDt["equal"], dtype=bool), np.uint8) if "equal" in readClassDt else None
+    rcw = c(readClassDt["rcWidth"], np.float64) if "rcWidth" in readClassDt else None
+    txlen = c(readClassDt["txlen"], np.float64) if "txlen" in readClassDt else None
+    cap = max(n, 1)
+    t_out = np.zeros(cap, np.int64)
+    c0, c1, c2 = np.zeros(cap), np.zeros(cap), np.zeros(cap)
+    k = ctypes.c_int64()
+    d = ctypes.c_double()
+    _lib.check_quant(L.bambu_quantDT(n, ptr(gene), ptr(tx), ptr(eq), ptr(nobs), ptr(equal), ptr(rcw), ptr(txlen),
+                                     int(bool(par["degradationBias"])), int(par["maxiter"]), float(par["minvalue"]),
+                                     float(par["conv"]), ptr(t_out), ptr(c0), ptr(c1), ptr(c2), ctypes.byref(k),
+                                     ctypes.byref(d)))
+    m = int(k.value)
+    return {"txid": t_out[:m], "counts": c0[:m], "fullLengthCounts": c1[:m], "uniqueCounts": c2[:m],
+            "d_rate": float(d.value)}
+
+
 # ------------------------------------------------------------------ the stage
 def bambu_quantDT(readClassDt, emParameters=None, verbose=False, em=None, details=None):
     """``bambu.quantDT`` (R/bambu-quantify.R:53-74).

@@ -150,6 +150,38 @@ int bambu_em_plan_last_run_launches(bambu_em_plan *plan, int32_t *n_launches);
 /* bytes of device memory held by the plan */
 int bambu_em_plan_device_bytes(bambu_em_plan *plan, int64_t *bytes);
 
+/* ---- the stage around the EM: bambu.quantDT (R/bambu-quantify.R:53-74), native host code ----------
+ * Long table: one row per (equivalence class, transcript) pair with the columns GENEID (any integer
+ * coding, e.g. match(GENEID, unique(GENEID))), txid, eqClassId, nobs, equal, rcWidth, txlen
+ * (R/bambu-quantify_utilityFunctions.R:199-203).  equal / rcWidth / txlen may be NULL (FALSE / 0 / 1).
+ *
+ * bambu_quant_pack_create = addAval ... removeUnObservedGenes, initialiseOutput, filterTxRc,
+ * assignGroups, getInputList (R/...utilityFunctions.R:196-371): the arena for bambu_em_batched plus the
+ * bookkeeping the merge needs.  bambu_quant_merge = modifyQuantOut + removeDuplicates (:438-455).
+ * bambu_quantDT = pack -> bambu_em_batched -> merge: the drop-in for bambu.quantDT. */
+typedef struct bambu_quant_pack bambu_quant_pack;
+const char *bambu_quant_last_error(void);
+int bambu_quant_pack_create(bambu_quant_pack **pack, int64_t n_rows, const int64_t *gene_code, const int64_t *txid,
+                            const int64_t *eqClassId, const double *nobs, const uint8_t *equal, const double *rcWidth,
+                            const double *txlen, int32_t degradation_bias);
+int bambu_quant_pack_free(bambu_quant_pack *pack);
+int bambu_quant_pack_sizes(const bambu_quant_pack *pack, int64_t *n_groups, int64_t *n_rows, int64_t *n_cols,
+                           int64_t *nnz, int64_t *n_out, int64_t *n_unobserved, double *d_rate);
+/* borrowed pointers, valid until bambu_quant_pack_free; any argument may be NULL */
+int bambu_quant_pack_arena(const bambu_quant_pack *pack, const int64_t **grp_row_ptr, const int64_t **grp_col_ptr,
+                           const int64_t **row_nnz_ptr, const int32_t **col_idx, const double **aval,
+                           const uint8_t **nz_flags, const double **Y, const double **K, const uint8_t **col_flags,
+                           const int32_t **txid);
+int bambu_quant_pack_bookkeeping(const bambu_quant_pack *pack, const int64_t **out_txid,
+                                 const int64_t **unobserved_txid, const int64_t **gene_grp_id);
+/* est: 3 x n_rows as returned by bambu_em_batched; outputs hold up to n_unobserved + n_out rows */
+int bambu_quant_merge(const bambu_quant_pack *pack, const double *est, int64_t *txid_out, double *counts,
+                      double *full_length, double *unique_counts, int64_t *n_result);
+int bambu_quantDT(int64_t n_rows, const int64_t *gene_code, const int64_t *txid, const int64_t *eqClassId,
+                  const double *nobs, const uint8_t *equal, const double *rcWidth, const double *txlen,
+                  int32_t degradation_bias, int32_t maxiter, double minvalue, double conv, int64_t *txid_out,
+                  double *counts, double *full_length, double *unique_counts, int64_t *n_result, double *d_rate);
+
 #ifdef __cplusplus
 }
 #endif
