@@ -501,8 +501,9 @@ static int slot_prepare(Slot &s, const int64_t *grp_row_ptr, const int64_t *grp_
     const int64_t rows = s.rows(), nnz = s.nnz(), cols = s.cols();
     // SELL pool: typical need is ~25 B per live entry + ~40 B per row / live column; grown on demand
     int64_t pool = (int64_t)(24.0 * (double)nnz + 48.0 * (double)(rows + cols)) + (4 << 20);
+    if (const char *e = getenv("BAMBU_EM_POOL_BYTES")) pool = std::max<int64_t>(atoll(e), 4096);   // tests: force the grow-and-rerun path
     pool = (pool + 15) / 16 * 16;
-    s.pool_bytes = std::max<int64_t>(pool, (int64_t)s.pool.cap / 16 * 16);
+    s.pool_bytes = getenv("BAMBU_EM_POOL_BYTES") ? pool : std::max<int64_t>(pool, (int64_t)s.pool.cap / 16 * 16);
     TRY(s.grp_row_ptr.ensure(8 * (size_t)(ng + 1), &s.device_bytes));
     TRY(s.grp_col_ptr.ensure(8 * (size_t)(ng + 1), &s.device_bytes));
     TRY(s.row_nnz_ptr.ensure(8 * (size_t)(rows + 1), &s.device_bytes));

@@ -277,3 +277,41 @@ def test_config3_scaled(em, oracle_mod):
     got = np.bincount(np.repeat(np.arange(a.n_groups), M), weights=est[0], minlength=a.n_groups)
     want = np.bincount(np.repeat(np.arange(a.n_groups), N), weights=a.K * a.Y, minlength=a.n_groups)
     assert np.allclose(got, want, rtol=1e-9)
+
+
+def test_image_pool_grows_and_reruns(em, oracle_mod, monkeypatch):
+    """The SELL images are bump-allocated on the device; when the pool is too small the kernels flag
+    it, the host doubles the pool and reruns the chunk -- results must not change."""
+    from bambu_b200 import synthetic
+    a = synthetic.config2(scale=0.03)
+    monkeypatch.setenv("BAMBU_EM_POOL_BYTES", "65536")
+    check_against_oracle(em, oracle_mod, a)
+    with em.EmPlan(a) as plan:
+        plan.upload()
+        plan.run()
+        est, iters, status = plan.download()
+    o_est, o_it, _ = oracle_mod.em_batched(a, mode=oracle_mod.MODE_SPARSE)
+    assert np.array_equal(iters, o_it)
+    assert_same_doubles(est, o_est, "after pool growth")
+
+
+def test_wide_group_routes_to_streamed_tier(em, oracle_mod):
+    """A group whose rows + columns exceed what 16-bit byte offsets can address (M + N > 8190) cannot
+    be shared-memory resident even though it is sparse; it must take the streamed tier."""
+    from bambu_b200.arena import Arena
+    rng = np.random.default_rng(123)
+    big = giant_locus_arena(rng, 60, 9000, 1.5)
+    a = Arena.concatenate([random_arena(rng, n_groups=5), big])
+    check_against_oracle(em, oracle_mod, a, maxiter=500)
+
+
+def test_giant_groups_in_small_chunks(em, oracle_mod, monkeypatch):
+    """streamed-tier groups inside the chunked pipeline (each chunk makes its own cooperative launch)"""
+    from bambu_b200.arena import Arena
+    rng = np.random.default_rng(321)
+    parts = []
+    for _ in range(3):
+        parts += [random_arena(rng, n_groups=8), giant_locus_arena(rng, 200, 6000, 12.0)]
+    a = Arena.concatenate(parts)
+    monkeypatch.setenv("BAMBU_EM_CHUNK_MB", "0.5")
+    check_against_oracle(em, oracle_mod, a, maxiter=300)
