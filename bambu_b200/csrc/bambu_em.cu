@@ -119,7 +119,7 @@ struct Ctrl {   // device control block, zeroed at the start of every run
     unsigned long long pool_ctr;
     int qcount[8];
     int ticket[8];
-    unsigned int gflags[128]; // streamed tier: [0..7] hazard / stopping flags, [64..65] grid barrier (own cache line)
+    unsigned int gflags[64 * 8]; // streamed tier, per team of CTAs: [0..7] hazard / stopping flags, [32..33] barrier
 };
 
 // ------------------------------------------------------------------------------
@@ -642,7 +642,12 @@ static int slot_enqueue(Slot &s)
         double *est = v.est;
         int32_t *iters = v.iters, *status = v.status;
         unsigned int *gflags = v.ctrl->gflags;
-        void *args[] = {&descs, &n_giant, &gbuf_c, &gbuf, &grp, &rows, &P, &est, &iters, &status, &gflags};
+        // loci are iterated by teams of CTAs (giant.cuh); more teams = more overlap, fewer warps per locus
+        int n_teams = 1;
+        if (const char *e = getenv("BAMBU_EM_GIANT_TEAMS")) n_teams = atoi(e);
+        else n_teams = (n_giant >= 8) ? 4 : (n_giant >= 2 ? 2 : 1);
+        n_teams = std::max(1, std::min(std::min(n_teams, 8), n_giant));
+        void *args[] = {&descs, &n_giant, &gbuf_c, &gbuf, &grp, &rows, &P, &est, &iters, &status, &gflags, &n_teams};
         // dynamic shared memory: one private copy of theta per CTA
         const size_t smem = std::max<size_t>(s.giant_smem, 1024);
         int per_sm = 0;

@@ -356,22 +356,27 @@ template <int T>
 __global__ void __launch_bounds__(T)
 em_giant_kernel(const GiantDesc *__restrict__ descs, int n_giant, const uint8_t *gbuf_c, uint8_t *gbuf,
                 const int64_t *__restrict__ grp_row_ptr, int64_t total_rows, EmParams P, double *__restrict__ est,
-                int32_t *__restrict__ iters, int32_t *__restrict__ status, unsigned int *gflags /* 8 words, zeroed */)
+                int32_t *__restrict__ iters, int32_t *__restrict__ status, unsigned int *gflags /* zeroed */,
+                int n_teams)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    unsigned int *bar = gflags + 64;  // arrival counter + generation, on a cache line of their own
-                                      // (148 CTAs poll it; the stopping flags must not share the line)
-    const unsigned int n_ctas = gridDim.x;
+    // The grid is split into n_teams teams of CTAs; a team iterates on one locus at a time with its
+    // own barrier, so the barrier / latency-bound stretches of one locus overlap with the work of the
+    // others.  Team t owns CTAs {t, t + n_teams, ...} and loci {t, t + n_teams, ...}.
+    const int team = blockIdx.x % n_teams, team_rank = blockIdx.x / n_teams;
+    const unsigned int n_ctas = (gridDim.x - team + n_teams - 1) / n_teams;      // CTAs of this team
+    unsigned int *tflags = gflags + 64 * team;      // per team: [0..7] flags, [32..33] barrier (own cache line)
+    unsigned int *bar = tflags + 32;
     double *theta = reinterpret_cast<double *>(smem);   // M, private copy per CTA
     const int tid = threadIdx.x, lane = tid & 31;
-    const int64_t gtid = (int64_t)blockIdx.x * T + tid, gthreads = (int64_t)gridDim.x * T;
+    const int64_t gtid = (int64_t)team_rank * T + tid, gthreads = (int64_t)n_ctas * T;   // team-relative
     // warp tasks are dealt round-robin over the CTAs (task w -> CTA w % n, warp w / n): a phase with
     // fewer tasks than warps then keeps every SM lightly and evenly loaded
     const int64_t gwarps = gthreads >> 5;
-    const int64_t gwarp = (int64_t)(tid >> 5) * gridDim.x + blockIdx.x;
+    const int64_t gwarp = (int64_t)(tid >> 5) * n_ctas + team_rank;
     (void)gbuf_c;
 
-    for (int gi = 0; gi < n_giant; ++gi) {
+    for (int gi = team; gi < n_giant; gi += n_teams) {
         const GiantDesc D = descs[gi];
         const int M = D.M, NL = D.NL;
         uint8_t *img = gbuf + D.base;
@@ -396,7 +401,7 @@ em_giant_kernel(const GiantDesc *__restrict__ descs, int n_giant, const uint8_t 
         uint32_t *cntS = reinterpret_cast<uint32_t *>(img + D.cntS);
         // [0..1] hazard by update parity, [2] inf-column count, [3] non-finite estimate,
         // [4..5] "delta > conv" by update parity, [6..7] non-finite theta count by update parity
-        unsigned int *hz = gflags;
+        unsigned int *hz = tflags;
         const int64_t row0 = grp_row_ptr[D.g];
         // per-warp staging of 2 x 32 products behind theta[M+1]
         double *stage = reinterpret_cast<double *>(smem + align_up(8u * (uint32_t)(M + 1), 16)) + 64 * (tid >> 5);
