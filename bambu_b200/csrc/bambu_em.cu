@@ -187,6 +187,13 @@ struct Slot {
     // device buffers (grow-only)
     DevBuf grp_row_ptr, grp_col_ptr, row_nnz_ptr, payload, img, img_off, info, pool, ginfo, queue, nnz_nonzero, est,
         iters, status, work, ctrl, gdesc, gbuf;
+    // per-group extents of the current chunk (host copy: the caller's arrays may be gone by the time a
+    // group has to be moved to the streamed tier)
+    std::vector<int32_t> hM, hN;
+    std::vector<int64_t> hE;
+    std::vector<GiantDesc> giants;   // streamed-tier groups of the current chunk (+ spilled ones)
+    int64_t giant_bytes = 0, giant_bytes_prepared = 0;
+    int n_giant_prepared = 0;
     // streamed tier (giant loci) of the current chunk
     int n_giant = 0;
     uint32_t giant_smem = 0;
@@ -301,7 +308,6 @@ static int pack_config_T()
 }
 
 constexpr int kGiantThreads = 1024;
-static int g_giant_grid_per_sm = 0;
 
 static bool force_giant()
 {
@@ -441,7 +447,9 @@ static int slot_prepare(Slot &s, const int64_t *grp_row_ptr, const int64_t *grp_
     std::vector<int64_t> gnnz((size_t)ng, 0);
     uint32_t smem_pack[8] = {}, smem_sell[8] = {};
     int64_t off = 0, goff = 0;
-    std::vector<GiantDesc> giants;
+    std::vector<GiantDesc> &giants = s.giants;
+    giants.clear();
+    s.hM.assign((size_t)ng, 0); s.hN.assign((size_t)ng, 0); s.hE.assign((size_t)ng, 0);
     uint32_t gsmem = 0;
     const bool forced_giant = force_giant();
     for (int64_t g = g0; g < g1; ++g) {
@@ -450,6 +458,7 @@ static int slot_prepare(Slot &s, const int64_t *grp_row_ptr, const int64_t *grp_
         const int64_t e = row_nnz_ptr[grp_row_ptr[g + 1]] - row_nnz_ptr[grp_row_ptr[g]];
         gnnz[g - g0] = e;
         img_off[g - g0] = off;
+        s.hM[g - g0] = (int32_t)std::min<int64_t>(M, INT32_MAX); s.hN[g - g0] = (int32_t)std::min<int64_t>(N, INT32_MAX); s.hE[g - g0] = e;
         if (M == 0) continue;
         if (M == 1 && s.single_tx_shortcut) { single.push_back((int32_t)g); continue; }
         const double ub = 20.0 * (double)e + 18.0 * (double)(M + N) + 64.0;
@@ -520,6 +529,8 @@ static int slot_prepare(Slot &s, const int64_t *grp_row_ptr, const int64_t *grp_
     TRY(s.ctrl.ensure(sizeof(Ctrl), &s.device_bytes));
     s.n_giant = (int)giants.size();
     s.giant_smem = gsmem;
+    s.giant_bytes = s.giant_bytes_prepared = goff;
+    s.n_giant_prepared = s.n_giant;
     if (s.n_giant) {
         TRY(s.h_gdesc.ensure(sizeof(GiantDesc) * giants.size()));
         memcpy(s.h_gdesc.p, giants.data(), sizeof(GiantDesc) * giants.size());
@@ -574,6 +585,47 @@ static int slot_upload(Slot &s, const int32_t *col_idx, const double *aval, cons
     return BAMBU_EM_OK;
 }
 
+// ---- streamed tier launches over descs [first, first + count) ---------------------------------
+static int launch_giant_pack(Slot &s, const SlotViews &v, int first, int count, cudaStream_t st)
+{
+    pack_giant_kernel<1024><<<count, 1024, 0, st>>>(v.A, s.gdesc.as<GiantDesc>() + first, count, s.gbuf.as<uint8_t>(),
+                                                     v.nnz_nonzero, &v.ctrl->err);
+    CUDA_TRY(cudaGetLastError());
+    s.launches += 1;
+    return BAMBU_EM_OK;
+}
+
+static int launch_giant_em(Slot &s, const SlotViews &v, int first, int count, cudaStream_t st)
+{
+    // cooperative launch: every CTA must be resident at once, so this runs after the resident
+    // classes have drained (ordered on the main stream)
+    const GiantDesc *descs = s.gdesc.as<GiantDesc>() + first;
+    int n_giant = count;
+    const uint8_t *gbuf_c = s.gbuf.as<uint8_t>();
+    uint8_t *gbuf = s.gbuf.as<uint8_t>();
+    const int64_t *grp = v.A.grp_row_ptr;
+    int64_t rows = s.rows();
+    EmParams P = s.P;
+    double *est = v.est;
+    int32_t *iters = v.iters, *status = v.status;
+    unsigned int *gflags = v.ctrl->gflags;
+    // loci are iterated by teams of CTAs (giant.cuh); more teams = more overlap, fewer warps per locus
+    int n_teams = 1;
+    if (const char *e = getenv("BAMBU_EM_GIANT_TEAMS")) n_teams = atoi(e);
+    else n_teams = (n_giant >= 8) ? 4 : (n_giant >= 2 ? 2 : 1);
+    n_teams = std::max(1, std::min(std::min(n_teams, 8), n_giant));
+    void *args[] = {&descs, &n_giant, &gbuf_c, &gbuf, &grp, &rows, &P, &est, &iters, &status, &gflags, &n_teams};
+    // dynamic shared memory: one private copy of theta per CTA + the per-warp staging
+    const size_t smem = std::max<size_t>(s.giant_smem, 1024);
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_giant_kernel<kGiantThreads>, kGiantThreads, smem));
+    if (per_sm < 1) return fail(BAMBU_EM_ECUDA, "streamed EM kernel does not fit an SM");
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void *)em_giant_kernel<kGiantThreads>, dim3(g_num_sms), dim3(kGiantThreads),
+                                         args, smem, st));
+    s.launches += 1;
+    return BAMBU_EM_OK;
+}
+
 static int slot_enqueue(Slot &s)
 {
     const SlotViews v = slot_views(s);
@@ -606,12 +658,9 @@ static int slot_enqueue(Slot &s)
     }
     if (s.n_giant) {   // streamed tier: pack now (one CTA per giant group), iterate after the resident classes
         CUDA_TRY(cudaStreamWaitEvent(s.giant_stream, s.ev_fork, 0));
-        pack_giant_kernel<1024><<<s.n_giant, 1024, 0, s.giant_stream>>>(v.A, s.gdesc.as<GiantDesc>(), s.n_giant,
-                                                                         s.gbuf.as<uint8_t>(), v.nnz_nonzero, &v.ctrl->err);
-        CUDA_TRY(cudaGetLastError());
+        TRY(launch_giant_pack(s, v, 0, s.n_giant, s.giant_stream));
         CUDA_TRY(cudaEventRecord(s.giant_packed, s.giant_stream));
         CUDA_TRY(cudaStreamWaitEvent(st, s.giant_packed, 0));
-        s.launches += 1;
     }
     CUDA_TRY(cudaEventRecord(s.ev_packed, st));
     if (any) {   // EM, one class per stream; the queues were filled on the device
@@ -622,41 +671,7 @@ static int slot_enqueue(Slot &s)
             CUDA_TRY(cudaStreamWaitEvent(st, s.em_done[c], 0));
         }
     }
-    if (s.n_giant) {
-        // cooperative launch: every CTA must be resident at once, so this runs after the resident
-        // classes have drained (ordered on the main stream)
-        if (!g_giant_grid_per_sm) {
-            int per_sm = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_giant_kernel<kGiantThreads>, kGiantThreads,
-                                                                   (size_t)kSmemMax));
-            if (per_sm < 1) return fail(BAMBU_EM_ECUDA, "streamed EM kernel does not fit an SM");
-            g_giant_grid_per_sm = per_sm;
-        }
-        const GiantDesc *descs = s.gdesc.as<GiantDesc>();
-        int n_giant = s.n_giant;
-        const uint8_t *gbuf_c = s.gbuf.as<uint8_t>();
-        uint8_t *gbuf = s.gbuf.as<uint8_t>();
-        const int64_t *grp = v.A.grp_row_ptr;
-        int64_t rows = s.rows();
-        EmParams P = s.P;
-        double *est = v.est;
-        int32_t *iters = v.iters, *status = v.status;
-        unsigned int *gflags = v.ctrl->gflags;
-        // loci are iterated by teams of CTAs (giant.cuh); more teams = more overlap, fewer warps per locus
-        int n_teams = 1;
-        if (const char *e = getenv("BAMBU_EM_GIANT_TEAMS")) n_teams = atoi(e);
-        else n_teams = (n_giant >= 8) ? 4 : (n_giant >= 2 ? 2 : 1);
-        n_teams = std::max(1, std::min(std::min(n_teams, 8), n_giant));
-        void *args[] = {&descs, &n_giant, &gbuf_c, &gbuf, &grp, &rows, &P, &est, &iters, &status, &gflags, &n_teams};
-        // dynamic shared memory: one private copy of theta per CTA
-        const size_t smem = std::max<size_t>(s.giant_smem, 1024);
-        int per_sm = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_giant_kernel<kGiantThreads>, kGiantThreads, smem));
-        per_sm = std::max(1, std::min(per_sm, 2));
-        CUDA_TRY(cudaLaunchCooperativeKernel((const void *)em_giant_kernel<kGiantThreads>, dim3(g_num_sms * per_sm),
-                                             dim3(kGiantThreads), args, smem, st));
-        s.launches += 1;
-    }
+    if (s.n_giant) TRY(launch_giant_em(s, v, 0, s.n_giant, st));
     CUDA_TRY(cudaEventRecord(s.ev_end, st));
     s.ran = true;
     s.finished = false;
@@ -681,22 +696,72 @@ static int slot_run(Slot &s, int32_t maxiter, double minvalue, double conv)
     return slot_enqueue(s);
 }
 
-// wait for the run; if the SELL pool was too small, grow it and run again
+// Groups the host admitted to the resident tier by their entry count can still need more than one
+// SM's shared memory once padded into slices (one very long line is enough).  The sell kernel
+// flags them instead of queueing them; here they are packed and iterated by the streamed tier.
+static int slot_spill_to_streamed(Slot &s)
+{
+    const size_t ng = (size_t)s.ng();
+    std::vector<GroupImg> gi(ng);
+    CUDA_TRY(cudaMemcpyAsync(gi.data(), s.ginfo.p, sizeof(GroupImg) * ng, cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    const int first = (int)s.giants.size();
+    for (size_t k = 0; k < ng; ++k) {
+        if (gi[k].cls != -1) continue;
+        const int64_t M = s.hM[k], N = s.hN[k], e = s.hE[k];
+        if (8 * (M + 1) + 16 + 512 * (kGiantThreads / 32) > (int64_t)kSmemMax)
+            return fail(BAMBU_EM_EINVAL, "group %lld (M=%lld) exceeds the streamed tier", (long long)(s.g0 + (int64_t)k), (long long)M);
+        GiantDesc d;
+        memset(&d, 0, sizeof d);
+        d.g = (int32_t)(s.g0 + (int64_t)k); d.M = (int32_t)M; d.N = (int32_t)N;
+        giant_layout(d, M, N, e);
+        d.base = s.giant_bytes;
+        s.giant_bytes += d.total;
+        s.giants.push_back(d);
+        s.giant_smem = std::max<uint32_t>(s.giant_smem, (uint32_t)(8 * (M + 1) + 16 + 512 * (kGiantThreads / 32)));
+    }
+    const int count = (int)s.giants.size() - first;
+    if (count == 0) return fail(BAMBU_EM_ECUDA, "device reported an oversized group but none is marked");
+    // the earlier streamed-tier groups are finished: their images may be dropped when the buffer grows
+    TRY(s.h_gdesc.ensure(sizeof(GiantDesc) * s.giants.size()));
+    memcpy(s.h_gdesc.p, s.giants.data(), sizeof(GiantDesc) * s.giants.size());
+    TRY(s.gdesc.ensure(sizeof(GiantDesc) * s.giants.size(), &s.device_bytes));
+    TRY(s.gbuf.ensure((size_t)s.giant_bytes, &s.device_bytes));
+    cudaStream_t st = s.stream;
+    CUDA_TRY(cudaMemcpyAsync(s.gdesc.p, s.h_gdesc.p, sizeof(GiantDesc) * s.giants.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(s.ctrl.p, 0, sizeof(Ctrl), st));      // error word, flags and barrier words
+    const SlotViews v = slot_views(s);
+    TRY(launch_giant_pack(s, v, first, count, st));
+    TRY(launch_giant_em(s, v, first, count, st));
+    CUDA_TRY(cudaEventRecord(s.ev_end, st));
+    s.n_giant = (int)s.giants.size();
+    return BAMBU_EM_OK;
+}
+
+// wait for the run; if the SELL pool was too small, grow it and run again; move groups whose padded
+// image exceeds shared memory to the streamed tier
 static int slot_finish(Slot &s)
 {
     if (!s.ran || s.finished) return BAMBU_EM_OK;
-    for (int attempt = 0; attempt < 8; ++attempt) {
+    for (int attempt = 0; attempt < 12; ++attempt) {
         int err = 0;
         CUDA_TRY(cudaMemcpyAsync(&err, &s.ctrl.as<Ctrl>()->err, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
         CUDA_TRY(cudaStreamSynchronize(s.stream));
         if (err == 0) { s.finished = true; return BAMBU_EM_OK; }
-        if (err == kErrColRange) return fail(BAMBU_EM_EINVAL, "col_idx outside its group's column range");
-        if (err == kErrColOrder) return fail(BAMBU_EM_EINVAL, "col_idx not strictly increasing inside a row");
-        if (err == kErrTooBig) return fail(BAMBU_EM_EINVAL, "a gene group's image exceeds the shared-memory resident tier");
-        if (err != kErrPool) return fail(BAMBU_EM_ECUDA, "device error word %d", err);
-        s.pool_bytes *= 2;
-        TRY(s.pool.ensure((size_t)s.pool_bytes, &s.device_bytes));
-        TRY(slot_enqueue(s));
+        if (err & kErrColRange) return fail(BAMBU_EM_EINVAL, "col_idx outside its group's column range");
+        if (err & kErrColOrder) return fail(BAMBU_EM_EINVAL, "col_idx not strictly increasing inside a row");
+        if (err & kErrPool) {
+            s.pool_bytes *= 2;
+            TRY(s.pool.ensure((size_t)s.pool_bytes, &s.device_bytes));
+            // a rerun starts from the chunk's own streamed-tier list again
+            s.giants.resize((size_t)s.n_giant_prepared);
+            s.n_giant = s.n_giant_prepared;
+            s.giant_bytes = s.giant_bytes_prepared;
+            TRY(slot_enqueue(s));
+            continue;
+        }
+        if (err & kErrTooBig) { TRY(slot_spill_to_streamed(s)); continue; }
+        return fail(BAMBU_EM_ECUDA, "device error word %d", err);
     }
     return fail(BAMBU_EM_ENOMEM, "SELL image pool kept overflowing");
 }

@@ -153,11 +153,12 @@ constexpr uint32_t kSmemMax = 227u * 1024u - 256u;  // per-CTA opt-in maximum mi
 constexpr int kMaxIndex = 32767;                    // u16 index carries a parity bit
 constexpr int kMaxVecElems = 8190;                  // M + NL of a resident group: byte offsets must fit u16
 
-// error codes written to the device error word by the kernels
+// condition bits OR-ed into the device error word by the kernels
 constexpr int kErrColRange = 1;   // col_idx outside [0, N)
 constexpr int kErrColOrder = 2;   // col_idx not strictly increasing inside a row
-constexpr int kErrPool = 3;       // image pool exhausted (the host grows it and reruns)
-constexpr int kErrTooBig = 4;     // a group's SELL image exceeds shared memory
+constexpr int kErrPool = 4;       // image pool exhausted (the host grows it and reruns)
+constexpr int kErrTooBig = 8;     // a group's SELL image exceeds shared memory (the host moves the group
+                                  // to the streamed tier)
 
 // ---- block-wide exclusive scan, in place, n arbitrary ---------------------------
 template <int T>
@@ -197,6 +198,35 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t *a, int n, uint32_t
     }
     __syncthreads();
     return total;
+}
+
+// In-place Shell sort (Ciura gaps) of one column's (row index, value) pairs by row index: the scatter
+// that builds a column leaves its entries in arbitrary order; arma::sum adds them by ascending row.
+// Columns are short (tens of entries) but nothing bounds them: O(L^1.3) keeps a column shared by
+// thousands of transcripts from stalling its thread for L^2 steps.
+template <typename IdxT>
+__device__ __forceinline__ void sort_column(IdxT *idx, double *val, uint32_t lo, uint32_t hi)
+{
+    const uint32_t n = hi - lo;
+    if (n < 2) return;
+    const uint32_t gaps[9] = {1750, 701, 301, 132, 57, 23, 10, 4, 1};
+#pragma unroll 1
+    for (int g = 0; g < 9; ++g) {
+        const uint32_t gap = gaps[g];
+        if (gap >= n) continue;
+        for (uint32_t p = lo + gap; p < hi; ++p) {
+            const IdxT kr = idx[p];
+            const double kv = val[p];
+            uint32_t q = p;
+            while (q >= lo + gap && idx[q - gap] > kr) {
+                idx[q] = idx[q - gap];
+                val[q] = val[q - gap];
+                q -= gap;
+            }
+            idx[q] = kr;
+            val[q] = kv;
+        }
+    }
 }
 
 __device__ __forceinline__ bool is_finite(double x) { return fabs(x) <= 1.7976931348623157e308; }

@@ -136,8 +136,8 @@ pack_giant_kernel(ArenaDev A, GiantDesc *__restrict__ descs, int n_giant, uint8_
         int prev = -1;
         for (int64_t k = rnp[i]; k < rnp[i + 1]; ++k) {
             const int j = A.col_idx[k];
-            if (j < 0 || j >= N) { atomicExch(err_flag, kErrColRange); continue; }
-            if (j <= prev) atomicExch(err_flag, kErrColOrder);
+            if (j < 0 || j >= N) { atomicOr(err_flag, kErrColRange); continue; }
+            if (j <= prev) atomicOr(err_flag, kErrColOrder);
             prev = j;
             const double a = A.aval[k];
             if (j & 1) a2 = __dadd_rn(a2, a); else a1 = __dadd_rn(a1, a);
@@ -192,21 +192,7 @@ pack_giant_kernel(ArenaDev A, GiantDesc *__restrict__ descs, int n_giant, uint8_
     }
     __syncthreads();
     // E: rows ascending inside every column
-    for (int j = tid; j < (int)NL; j += T) {
-        const uint32_t lo = cp[j], hi = cp[j + 1];
-        for (uint32_t p = lo + 1; p < hi; ++p) {
-            const uint32_t kr = ridx[p];
-            const double kv = rval[p];
-            uint32_t q = p;
-            while (q > lo && ridx[q - 1] > kr) {
-                ridx[q] = ridx[q - 1];
-                rval[q] = rval[q - 1];
-                --q;
-            }
-            ridx[q] = kr;
-            rval[q] = kv;
-        }
-    }
+    for (int j = tid; j < (int)NL; j += T) sort_column(ridx, rval, cp[j], cp[j + 1]);
     __syncthreads();
     // F: column side in SELL order.  colmap/colcnt/cursor are free now: reuse them as
     //    len[NL] (colmap), histogram (shared), position -> column (ccol)

@@ -57,7 +57,7 @@ pack_resident_kernel(ArenaDev A, const int32_t *__restrict__ work, int n_work,
             uint32_t nz = 0;
             for (int64_t k = rnp[0]; k < rnp[1]; ++k) {
                 const int j = A.col_idx[k];
-                if (j < 0 || j >= N) { atomicExch(err_flag, kErrColRange); break; }
+                if (j < 0 || j >= N) { atomicOr(err_flag, kErrColRange); break; }
                 const double a = A.aval[k];
                 nz += (a != 0.0);
                 const double ky = __dmul_rn(A.K[col0 + j], A.Y[col0 + j]);
@@ -106,8 +106,8 @@ pack_resident_kernel(ArenaDev A, const int32_t *__restrict__ work, int n_work,
         int prev = -1;
         for (int64_t k = rnp[i]; k < rnp[i + 1]; ++k) {
             const int j = A.col_idx[k];
-            if (j < 0 || j >= N) { atomicExch(err_flag, kErrColRange); continue; }
-            if (j <= prev) atomicExch(err_flag, kErrColOrder);
+            if (j < 0 || j >= N) { atomicOr(err_flag, kErrColRange); continue; }
+            if (j <= prev) atomicOr(err_flag, kErrColOrder);
             prev = j;
             const double a = A.aval[k];
             if (j & 1) a2 = __dadd_rn(a2, a); else a1 = __dadd_rn(a1, a);
@@ -192,21 +192,7 @@ pack_resident_kernel(ArenaDev A, const int32_t *__restrict__ work, int n_work,
     __syncthreads();
 
     // ---- E: rows ascending inside every column (the order arma::sum adds them) --
-    for (int j = tid; j < (int)NL; j += T) {
-        const uint32_t lo = colcnt[j], hi = colcnt[j + 1];
-        for (uint32_t p = lo + 1; p < hi; ++p) {
-            const uint16_t kr = img_ridx[p];
-            const double kv = img_rval[p];
-            uint32_t q = p;
-            while (q > lo && img_ridx[q - 1] > kr) {
-                img_ridx[q] = img_ridx[q - 1];
-                img_rval[q] = img_rval[q - 1];
-                --q;
-            }
-            img_ridx[q] = kr;
-            img_rval[q] = kv;
-        }
-    }
+    for (int j = tid; j < (int)NL; j += T) sort_column(img_ridx, img_rval, colcnt[j], colcnt[j + 1]);
     if (tid == 0) {
         info[g].NL = (int32_t)NL;
         info[g].nnzL = (int32_t)nnzL;

@@ -162,7 +162,7 @@ sell_kernel(const int32_t *__restrict__ work, int n_work, const int64_t *__restr
         unsigned long long off = atomicAdd(pool_ctr, (unsigned long long)L.total);
         if (off + L.total > pool_bytes) {
             off = ~0ull;
-            atomicExch(err_flag, kErrPool);
+            atomicOr(err_flag, kErrPool);
         }
         s_off = off;
     }
@@ -215,7 +215,7 @@ sell_kernel(const int32_t *__restrict__ work, int n_work, const int64_t *__restr
         if (c == kNumClasses) {
             gi.cls = -1;
             gi.smem_bytes = 0;
-            atomicExch(err_flag, kErrTooBig);
+            atomicOr(err_flag, kErrTooBig);
         } else {
             gi.cls = c;
             const int pos = atomicAdd(&qcount[c], 1);

@@ -315,3 +315,28 @@ def test_giant_groups_in_small_chunks(em, oracle_mod, monkeypatch):
     a = Arena.concatenate(parts)
     monkeypatch.setenv("BAMBU_EM_CHUNK_MB", "0.5")
     check_against_oracle(em, oracle_mod, a, maxiter=300)
+
+
+def test_long_shared_columns(em, oracle_mod):
+    """Read classes compatible with (almost) every transcript of a locus: columns with thousands of
+    entries, in the resident tier (one group of 2000 transcripts) and in the streamed tier."""
+    from bambu_b200.arena import Arena
+    rng = np.random.default_rng(55)
+
+    def locus(M, n_wide, n_unique):
+        N = n_wide + n_unique
+        rows = np.concatenate([np.repeat(np.arange(M), n_wide), rng.integers(0, M, n_unique)])
+        cols = np.concatenate([np.tile(np.arange(n_wide), M), n_wide + np.arange(n_unique)])
+        keep = rng.random(len(rows)) < 0.97
+        keep[M * n_wide:] = True
+        key = np.unique(rows[keep].astype(np.int64) * N + cols[keep])
+        r, c = key // N, key % N
+        aval = rng.uniform(0.05, 1.0, len(key))
+        nobs = 1.0 + rng.negative_binomial(0.5, 0.5 / 40.5, N)
+        K = nobs.sum()
+        rnp = np.concatenate(([0], np.cumsum(np.bincount(r, minlength=M)))).astype(np.int64)
+        return Arena(np.array([0, M], np.int64), np.array([0, N], np.int64), rnp, c.astype(np.int32), aval,
+                     (rng.random(len(key)) < 0.2).astype(np.uint8), nobs / K, np.full(N, K),
+                     (np.bincount(c, minlength=N) > 1).astype(np.uint8), np.arange(M, dtype=np.int32))
+    a = Arena.concatenate([locus(2000, 2, 2100), locus(3000, 12, 4000), random_arena(rng, n_groups=4)])
+    check_against_oracle(em, oracle_mod, a, maxiter=120)
