@@ -80,6 +80,10 @@ static int ensure_device()
     return BAMBU_EM_OK;
 }
 
+// for quant_dev.cu (the device packer shares the device selection and its checks)
+int bambu_em_internal_ensure_device() { return ensure_device(); }
+void bambu_quant_release_workspace();
+
 // ------------------------------------------------------------------------------
 // size classes
 // ------------------------------------------------------------------------------
@@ -816,6 +820,7 @@ int bambu_em_shutdown(void)
         for (Slot &s : g_pipe) slot_destroy(s);
         g_pipe_used = false;
     }
+    bambu_quant_release_workspace();
     return BAMBU_EM_OK;
 }
 

@@ -22,10 +22,13 @@
 #include <vector>
 
 #include "../../include/bambu_em.h"
+#include "quant_pack.h"
 
 namespace {
 
-typedef long double ld;
+using qp::ld;
+using qp::bits_for;
+using qp::r_median;
 
 thread_local std::string g_pack_error;
 
@@ -34,13 +37,6 @@ struct KV {
     uint64_t k;
     uint32_t v;
 };
-
-inline int bits_for(uint64_t max_value)      // bits needed to hold values 0..max_value
-{
-    int b = 1;
-    while (b < 64 && (max_value >> b)) ++b;
-    return b;
-}
 
 void radix_kv(std::vector<KV> &a, int key_bits)
 {
@@ -133,31 +129,9 @@ uint32_t pair_ids(const std::vector<uint32_t> &a, const std::vector<uint32_t> &b
 inline double r_pmax(double a, double b) { return (std::isnan(a) || std::isnan(b)) ? NAN : (a > b ? a : b); }
 inline double r_pmin(double a, double b) { return (std::isnan(a) || std::isnan(b)) ? NAN : (a < b ? a : b); }
 
-double r_median(std::vector<double> x)   // median(x, na.rm = TRUE) with mean()'s long double refinement
-{
-    x.erase(std::remove_if(x.begin(), x.end(), [](double v) { return std::isnan(v); }), x.end());
-    std::sort(x.begin(), x.end());
-    const size_t n = x.size();
-    if (!n) return NAN;
-    if (n & 1) return x[n / 2];
-    const ld a = x[n / 2 - 1], b = x[n / 2];
-    const ld s = (a + b) / (ld)2;
-    const ld t = ((a - s) + (b - s)) / (ld)2;
-    return (double)(s + t);
-}
-
 }  // namespace
 
-struct bambu_quant_pack {
-    // the arena
-    std::vector<int64_t> grp_row_ptr, grp_col_ptr, row_nnz_ptr;
-    std::vector<int32_t> col_idx, txid;
-    std::vector<double> aval, Y, K;
-    std::vector<uint8_t> nz_flags, col_flags;
-    // bookkeeping of initialiseOutput / removeUnObservedGenes / assignGroups
-    std::vector<int64_t> out_txid, unobserved_txid, gene_grp_id;
-    double d_rate = NAN;
-};
+void bambu_quant_set_error(const std::string &s) { g_pack_error = s; }      // for quant_dev.cu
 
 extern "C" {
 
@@ -234,16 +208,9 @@ int bambu_quant_pack_create(bambu_quant_pack **out, int64_t n, const int64_t *ge
                 const double L = txlen ? txlen[i] : 1.0;
                 if (L > glen[g]) glen[g] = L;
             }
-            std::vector<double> vals_keep, vals_all;
-            for (uint32_t g = 0; g < G; ++g) {
-                if (!has[g]) continue;
-                const double nb = (double)gnobs[g];
-                const double db = has_par[g] ? (double)gdobs[g] : NAN;
-                const double v = (db / nb) * 1000 / glen[g];
-                vals_all.push_back(v);
-                if (nb >= 30 && (nb - db) >= 5) vals_keep.push_back(v);     // NA comparisons are not TRUE
-            }
-            d_rate = r_median(vals_keep.empty() ? vals_all : vals_keep);
+            std::vector<double> nb(G), db(G);      // every gene code owns at least one row, so has[] is all ones
+            for (uint32_t g = 0; g < G; ++g) { nb[g] = (double)gnobs[g]; db[g] = (double)gdobs[g]; }
+            d_rate = qp::degradation_rate(G, nb.data(), db.data(), has_par.data(), glen.data());
         }
         P->d_rate = d_rate;
 
@@ -341,27 +308,11 @@ int bambu_quant_pack_create(bambu_quant_pack **out, int64_t n, const int64_t *ge
                 if (!seen_c[cls[i]]) { seen_c[cls[i]] = 1; ++n_eq[gene[i]]; }
             }
         }
-        std::vector<uint32_t> genes;     // kept genes, ascending gene_sid (= table order after filterTxRc's arrange)
-        for (uint32_t g = 0; g < G; ++g) if (n_tx[g]) genes.push_back(g);
-        std::vector<int64_t> grp_of_gene(G, 0);
-        {
-            std::vector<uint64_t> dim(genes.size());
-            for (size_t k = 0; k < genes.size(); ++k) dim[k] = (uint64_t)n_tx[genes[k]] * n_eq[genes[k]];
-            std::vector<uint32_t> order(genes.size());
-            for (size_t k = 0; k < order.size(); ++k) order[k] = (uint32_t)k;
-            std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return dim[a] < dim[b]; });
-            uint64_t cum = 0;
-            for (uint32_t k : order) { cum += dim[k]; grp_of_gene[genes[k]] = (int64_t)(cum / 1000 + 1); }
-        }
+        std::vector<uint32_t> gi_of_gene;
+        const std::vector<int64_t> gids = qp::assign_groups(n_tx, n_eq, gi_of_gene);
         lap("assignGroups");
         // ---- getInputList + getAMat (:359-371, 427-431) as one arena --------------------------------
-        std::vector<int64_t> gids;
-        for (uint32_t g : genes) gids.push_back(grp_of_gene[g]);
-        std::sort(gids.begin(), gids.end());
-        gids.erase(std::unique(gids.begin(), gids.end()), gids.end());
         const uint32_t NG = (uint32_t)gids.size();
-        std::vector<uint32_t> gi_of_gene(G, 0);
-        for (uint32_t g : genes) gi_of_gene[g] = (uint32_t)(std::lower_bound(gids.begin(), gids.end(), grp_of_gene[g]) - gids.begin());
         std::vector<uint32_t> gi(N, 0);
         for (uint32_t i : rows) gi[i] = gi_of_gene[gene[i]];
         // arena rows: unique (group, txid) ascending; arena columns: unique (group, gene_sid, eqClassId) ascending
@@ -537,9 +488,11 @@ int bambu_quant_merge(const bambu_quant_pack *p, const double *est, int64_t *txi
     return BAMBU_EM_OK;
 }
 
-// bambu.quantDT in one call: long table in, estimates by txid out (pack -> bambu_em_batched -> merge).
+// bambu.quantDT in one call with the HOST packer: long table in, estimates by txid out
+// (pack -> bambu_em_batched -> merge).  bambu_quantDT (quant_dev.cu) packs on the GPU and comes here for the
+// tables its device formulation does not cover.
 // Output arrays must hold at least as many rows as there are distinct txids in the input (<= n).
-int bambu_quantDT(int64_t n, const int64_t *gene_code, const int64_t *txid, const int64_t *eqClassId, const double *nobs,
+int bambu_quantDT_hostpack(int64_t n, const int64_t *gene_code, const int64_t *txid, const int64_t *eqClassId, const double *nobs,
                   const uint8_t *equal, const double *rcWidth, const double *txlen, int32_t degradation_bias,
                   int32_t maxiter, double minvalue, double conv, int64_t *txid_out, double *counts, double *full_length,
                   double *unique_counts, int64_t *n_result, double *d_rate_out)

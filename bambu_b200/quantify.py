@@ -278,10 +278,12 @@ def _gene_codes(gid):
     return np.unique(gid, return_inverse=True)[1].astype(np.int64)
 
 
-def pack_quantDT_native(readClassDt, emParameters=None) -> PackedQuant:
+def pack_quantDT_native(readClassDt, emParameters=None, gpu=False) -> PackedQuant:
     """The same as :func:`pack_quantDT`, done by the native packer of ``libbambu_em.so``
     (``bambu_quant_pack_create``, csrc/quant_pack.cpp) -- radix sorts and linear passes instead of
-    numpy group-bys; ~40x faster on a 2M-row sample.  Identical output (tests/test_quant_pack.py)."""
+    numpy group-bys; ~40x faster on a 2M-row sample.  Identical output (tests/test_quant_pack.py).
+    ``gpu=True``: the device packer (``bambu_quant_pack_create_gpu``, csrc/quant_dev.cu), arena copied back;
+    the result carries ``used_device`` (False when the table went through the host packer)."""
     import ctypes
     from . import _lib
     par = setEmParameters(emParameters)
@@ -300,8 +302,15 @@ def pack_quantDT_native(readClassDt, emParameters=None) -> PackedQuant:
     rcw = c(readClassDt["rcWidth"], np.float64) if "rcWidth" in readClassDt else None
     txlen = c(readClassDt["txlen"], np.float64) if "txlen" in readClassDt else None
     h = ctypes.c_void_p()
-    rc = L.bambu_quant_pack_create(ctypes.byref(h), n, ptr(gene), ptr(tx), ptr(eq), ptr(nobs), ptr(equal), ptr(rcw),
-                                   ptr(txlen), int(bool(par["degradationBias"])))
+    used = ctypes.c_int32(0)
+    if gpu:
+        rc = L.bambu_quant_pack_create_gpu(ctypes.byref(h), n, ptr(gene), ptr(tx), ptr(eq), ptr(nobs), ptr(equal),
+                                           ptr(rcw), ptr(txlen), int(bool(par["degradationBias"])), ctypes.byref(used))
+        if rc not in (0, _lib.EINVAL):
+            _lib.check_quant(rc)
+    else:
+        rc = L.bambu_quant_pack_create(ctypes.byref(h), n, ptr(gene), ptr(tx), ptr(eq), ptr(nobs), ptr(equal), ptr(rcw),
+                                       ptr(txlen), int(bool(par["degradationBias"])))
     if rc:
         raise ValueError(L.bambu_quant_last_error().decode())
     try:
@@ -328,14 +337,16 @@ def pack_quantDT_native(readClassDt, emParameters=None) -> PackedQuant:
         out.unobserved_txid = arr(bs[1], n_uo, np.int64)
         out.gene_grp_id = arr(bs[2], ng, np.int64)
         out.d_rate = float(d.value)
+        out.used_device = bool(used.value)
     finally:
         L.bambu_quant_pack_free(h)
     return out
 
 
-def bambu_quantDT_native(readClassDt, emParameters=None):
-    """``bambu.quantDT`` as ONE call into the library (``bambu_quantDT``: native pack -> CUDA EM ->
-    native merge).  Returns the same dict as :func:`bambu_quantDT` plus ``d_rate``."""
+def bambu_quantDT_native(readClassDt, emParameters=None, host_pack=False):
+    """``bambu.quantDT`` as ONE call into the library (``bambu_quantDT``: table to the GPU, device pack, CUDA EM
+    on the arena where it lies, native merge; ``host_pack=True`` = ``bambu_quantDT_hostpack``, the host packer
+    in front of ``bambu_em_batched``).  Returns the same dict as :func:`bambu_quantDT` plus ``d_rate``."""
     import ctypes
     from . import _lib
     par = setEmParameters(emParameters)
@@ -356,10 +367,10 @@ def bambu_quantDT_native(readClassDt, emParameters=None):
     c0, c1, c2 = np.zeros(cap), np.zeros(cap), np.zeros(cap)
     k = ctypes.c_int64()
     d = ctypes.c_double()
-    _lib.check_quant(L.bambu_quantDT(n, ptr(gene), ptr(tx), ptr(eq), ptr(nobs), ptr(equal), ptr(rcw), ptr(txlen),
-                                     int(bool(par["degradationBias"])), int(par["maxiter"]), float(par["minvalue"]),
-                                     float(par["conv"]), ptr(t_out), ptr(c0), ptr(c1), ptr(c2), ctypes.byref(k),
-                                     ctypes.byref(d)))
+    fn = L.bambu_quantDT_hostpack if host_pack else L.bambu_quantDT
+    _lib.check_quant(fn(n, ptr(gene), ptr(tx), ptr(eq), ptr(nobs), ptr(equal), ptr(rcw), ptr(txlen),
+                        int(bool(par["degradationBias"])), int(par["maxiter"]), float(par["minvalue"]),
+                        float(par["conv"]), ptr(t_out), ptr(c0), ptr(c1), ptr(c2), ctypes.byref(k), ctypes.byref(d)))
     m = int(k.value)
     return {"txid": t_out[:m], "counts": c0[:m], "fullLengthCounts": c1[:m], "uniqueCounts": c2[:m],
             "d_rate": float(d.value)}

@@ -142,7 +142,7 @@ def _giant_class_entries(m_g, n_free, k_mean, rng):
 
 
 def sample_arena(ann: Annotation, sample: int = 0, d_rate: float | None = 0.1, resample_frac: float = 0.0,
-                 observed_frac: float = 0.4, seed: int | None = None) -> Arena:
+                 observed_frac: float = 0.4, seed: int | None = None, long_table: bool = False):
     """One sample's arena.  ``sample`` seeds the counts; the pattern is the
     annotation's base pattern (seed ``ann.seed``) with ``resample_frac`` of the
     free classes re-drawn for this sample; ``d_rate=None`` draws U(0.02, 0.3)."""
@@ -235,6 +235,18 @@ def sample_arena(ann: Annotation, sample: int = 0, d_rate: float | None = 0.1, r
     Kg = np.bincount(gene_of_col, weights=nobs, minlength=G)
     K = Kg[gene_of_col]
     Y = nobs / K
+
+    if long_table:
+        # the same sample as the long table bambu.quantDT starts from (R/bambu-quantify.R:53-56):
+        # one row per (class, transcript), rows in random order.  txlen is drawn so that the
+        # a-values differ from the arena's (the degradation rate is estimated from the table).
+        trng = np.random.default_rng(ann.seed + 104_729)
+        txlen = trng.integers(400, 6000, int(m.sum())).astype(np.float64)
+        perm = rng.permutation(len(ecol))
+        return {"GENEID": eg[perm].astype(np.int64), "txid": (erow[perm] + 1).astype(np.int64),
+                "eqClassId": (ecol[perm] + 1).astype(np.int64), "nobs": nobs[ecol[perm]],
+                "equal": equal[perm], "rcWidth": np.minimum(w_col[ecol[perm]], txlen[erow[perm]]),
+                "txlen": txlen[erow[perm]]}
 
     # ---- arrange genes group by group ---------------------------------------
     gorder = np.lexsort((np.arange(G), ann.grp))   # by group id, then gene_sid

@@ -181,6 +181,18 @@ int bambu_quantDT(int64_t n_rows, const int64_t *gene_code, const int64_t *txid,
                   const double *nobs, const uint8_t *equal, const double *rcWidth, const double *txlen,
                   int32_t degradation_bias, int32_t maxiter, double minvalue, double conv, int64_t *txid_out,
                   double *counts, double *full_length, double *unique_counts, int64_t *n_result, double *d_rate);
+/* The same with the table packed by the host code of bambu_quant_pack_create (bambu_quantDT packs on the GPU and
+ * uses this for tables its device formulation does not cover: non-integer or negative nobs, negative or
+ * non-finite widths / lengths, a degradation rate that is not a finite number >= 0). */
+int bambu_quantDT_hostpack(int64_t n_rows, const int64_t *gene_code, const int64_t *txid, const int64_t *eqClassId,
+                  const double *nobs, const uint8_t *equal, const double *rcWidth, const double *txlen,
+                  int32_t degradation_bias, int32_t maxiter, double minvalue, double conv, int64_t *txid_out,
+                  double *counts, double *full_length, double *unique_counts, int64_t *n_result, double *d_rate);
+/* bambu_quant_pack_create done by the GPU (csrc/quant_dev.cu), the arena copied back into a host pack object.
+ * used_device (may be NULL) receives 1, or 0 when the table went through the host packer (see above). */
+int bambu_quant_pack_create_gpu(bambu_quant_pack **pack, int64_t n_rows, const int64_t *gene_code, const int64_t *txid,
+                                const int64_t *eqClassId, const double *nobs, const uint8_t *equal, const double *rcWidth,
+                                const double *txlen, int32_t degradation_bias, int32_t *used_device);
 
 #ifdef __cplusplus
 }
