@@ -26,6 +26,7 @@ SYMBOLS = {
     "bambu_em_batched": (ctypes.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _f64, _f64, _p, _p, _p]),
     "bambu_emWithL1": (ctypes.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _f64, _f64, _p, _p]),
     "bambu_em_plan_create": (ctypes.c_int, [ctypes.POINTER(_p), _i64, _p, _p, _p]),
+    "bambu_em_plan_reset": (ctypes.c_int, [_p, _i64, _p, _p, _p]),
     "bambu_em_plan_destroy": (ctypes.c_int, [_p]),
     "bambu_em_plan_set_stream": (ctypes.c_int, [_p, _p]),
     "bambu_em_plan_upload": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p]),

@@ -879,6 +879,21 @@ int bambu_em_plan_create(bambu_em_plan **out, int64_t n_groups, const int64_t *g
     return plan_create_impl(out, n_groups, grp_row_ptr, grp_col_ptr, row_nnz_ptr, true);
 }
 
+int bambu_em_plan_reset(bambu_em_plan *p, int64_t n_groups, const int64_t *grp_row_ptr, const int64_t *grp_col_ptr,
+                        const int64_t *row_nnz_ptr)
+{
+    if (!p) return fail(BAMBU_EM_EINVAL, "plan is NULL");
+    TRY(check_arrays(n_groups, grp_row_ptr, grp_col_ptr, row_nnz_ptr));
+    TRY(ensure_device());
+    Slot &s = p->slot;
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    s.payload_bound = s.payload_ready = false;
+    p->n_groups = n_groups;
+    TRY(slot_prepare(s, grp_row_ptr, grp_col_ptr, row_nnz_ptr, 0, n_groups));
+    if (cudaStreamSynchronize(s.stream) != cudaSuccess) return fail(BAMBU_EM_ECUDA, "structure upload failed");
+    return BAMBU_EM_OK;
+}
+
 int bambu_em_plan_set_stream(bambu_em_plan *p, void *cuda_stream)
 {
     if (!p) return fail(BAMBU_EM_EINVAL, "plan is NULL");

@@ -11,7 +11,9 @@
 #include <cstdlib>
 #include <new>
 #include <algorithm>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -185,7 +187,52 @@ __global__ void __launch_bounds__(kThreads) sort_scatter_kernel(const uint64_t *
     }
 }
 
+// The table columns come from pageable host memory, where a copy call returns only once the data is staged
+// (one host thread moves ~6 GB/s that way): one helper thread per column feeds the copy engines on its own
+// stream, while the calling thread already launches the passes over the columns that have arrived.
+struct Uploader {
+    struct Col { void *dst; const void *src; size_t bytes; };
+    Col cols[qd::kNumCols] = {};
+    cudaEvent_t ev[qd::kNumCols] = {};
+    cudaStream_t st[qd::kNumCols] = {};
+    std::atomic<int> issued[qd::kNumCols];
+    std::atomic<int> error{0};
+    std::thread th[qd::kNumCols];
+    double done_ms[qd::kNumCols] = {};
+    std::chrono::steady_clock::time_point t0;
+    int device = 0;
+    Uploader() { for (auto &i : issued) i.store(0); }
+    void start()
+    {
+        for (int c = 0; c < qd::kNumCols; ++c) QD_CUDA(cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming));
+        t0 = std::chrono::steady_clock::now();
+        for (int c = 0; c < qd::kNumCols; ++c) {
+            if (!cols[c].bytes) {        // nothing to copy: the event stays unrecorded, waiting on it is a no-op
+                issued[c].store(1, std::memory_order_release);
+                continue;
+            }
+            th[c] = std::thread([this, c] {
+                cudaError_t e = cudaSetDevice(device);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(cols[c].dst, cols[c].src, cols[c].bytes, cudaMemcpyHostToDevice, st[c]);
+                if (e == cudaSuccess) e = cudaEventRecord(ev[c], st[c]);
+                if (e != cudaSuccess) error.store((int)e);
+                done_ms[c] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                issued[c].store(1, std::memory_order_release);
+            });
+        }
+    }
+    void finish()
+    {
+        for (int c = 0; c < qd::kNumCols; ++c)
+            if (th[c].joinable()) { th[c].join(); cudaStreamSynchronize(st[c]); }
+        for (int c = 0; c < qd::kNumCols; ++c) if (ev[c]) { cudaEventDestroy(ev[c]); ev[c] = nullptr; }
+    }
+    ~Uploader() { finish(); }
+};
+
 struct CudaExec {
+    Uploader *up = nullptr;
+    bool have[qd::kNumCols] = {};
     cudaStream_t st = nullptr;
     uint8_t *pool = nullptr;
     size_t cap = 0, top = 0;
@@ -202,6 +249,26 @@ struct CudaExec {
         T *p = reinterpret_cast<T *>(pool + top);
         top += bytes;
         return p;
+    }
+    // order everything launched from here on behind the arrival of table column c
+    void need(int c)
+    {
+        if (!up || have[c]) return;
+        while (!up->issued[c].load(std::memory_order_acquire)) std::this_thread::yield();
+        if (up->error.load()) throw CudaError{(cudaError_t)up->error.load(), "copy of the table to the device"};
+        QD_CUDA(cudaStreamWaitEvent(st, up->ev[c], 0));
+        have[c] = true;
+    }
+    // BAMBU_PACK_TIMING: wall time of each stage of the pipeline (drains the stream, so it perturbs the total)
+    bool timing = false;
+    std::chrono::steady_clock::time_point t_lap;
+    void lap(const char *what)
+    {
+        if (!timing) return;
+        cudaStreamSynchronize(st);
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[device pack] %-30s %7.2f ms\n", what, std::chrono::duration<double, std::milli>(t - t_lap).count());
+        t_lap = t;
     }
     size_t mark() const { return top; }
     void release(size_t m) { top = m; }
@@ -284,7 +351,7 @@ struct CudaExec {
 struct Workspace {
     uint8_t *pool = nullptr;
     size_t cap = 0;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, up_st[qd::kNumCols] = {};
     int sms = 148;
     int device = -1;
     bool ensure(size_t bytes)
@@ -297,6 +364,8 @@ struct Workspace {
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         }
         if (!st && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return false;
+        for (auto &u : up_st)
+            if (!u && cudaStreamCreateWithFlags(&u, cudaStreamNonBlocking) != cudaSuccess) return false;
         if (bytes <= cap) return true;
         if (pool) cudaFree(pool);
         pool = nullptr;
@@ -309,10 +378,12 @@ struct Workspace {
     {
         if (pool) cudaFree(pool);
         if (st) cudaStreamDestroy(st);
+        for (auto &u : up_st) { if (u) cudaStreamDestroy(u); u = nullptr; }
         pool = nullptr; cap = 0; st = nullptr; device = -1;
     }
 };
 Workspace g_ws;
+bambu_em_plan *g_plan = nullptr;      // bambu_quantDT's cached plan
 
 size_t workspace_bytes(size_t n) { return n * 288 + (64u << 20); }
 
@@ -336,17 +407,37 @@ int run_device_pack(qdcuda::CudaExec &x, int64_t n, const int64_t *gene, const i
     qd::Input in;
     in.n = N;
     in.d_mode = d_mode;
-    auto up = [&](auto *src, bool need) -> decltype(src) {
+    qdcuda::Uploader up;
+    for (int c = 0; c < qd::kNumCols; ++c) up.st[c] = qdcuda::g_ws.up_st[c];
+    QD_CUDA(cudaGetDevice(&up.device));
+    auto col = [&](int c, auto *src, bool wanted) -> decltype(src) {
         typedef typename std::remove_const<typename std::remove_pointer<decltype(src)>::type>::type T;
-        if (!src || !need || !N) return nullptr;
+        if (!src || !wanted || !N) return nullptr;
         T *d = x.alloc<T>(N);
-        QD_CUDA(cudaMemcpyAsync(d, src, N * sizeof(T), cudaMemcpyHostToDevice, x.st));
+        up.cols[c] = qdcuda::Uploader::Col{d, src, N * sizeof(T)};
         return d;
     };
-    in.gene = up(gene, true); in.tx = up(tx, true); in.eq = up(eq, true); in.nobs = up(nobs, true);
-    in.equal = up(equal, true); in.rcw = up(rcw, d_mode); in.txl = up(txl, d_mode);
+    in.gene = col(qd::kColGene, gene, true); in.tx = col(qd::kColTx, tx, true); in.eq = col(qd::kColEq, eq, true);
+    in.nobs = col(qd::kColNobs, nobs, true); in.equal = col(qd::kColEqual, equal, true);
+    in.txl = col(qd::kColTxlen, txl, d_mode); in.rcw = col(qd::kColRcWidth, rcw, d_mode);
+    up.start();
+    x.up = &up;
+    x.timing = getenv("BAMBU_PACK_TIMING") != nullptr;
+    x.t_lap = std::chrono::steady_clock::now();
+    struct Detach {      // the thread is joined (Uploader's destructor) before the executor forgets it
+        qdcuda::CudaExec &x;
+        ~Detach() { x.up = nullptr; }
+    } detach{x};
     std::string err;
     const int rc = qd::pack(x, in, R, err);
+    const auto t_pack = std::chrono::steady_clock::now();
+    up.finish();
+    if (getenv("BAMBU_PACK_TIMING")) {
+        fprintf(stderr, "[device pack] pipeline done at %.2f ms; column copies staged at", std::chrono::duration<double, std::milli>(t_pack - up.t0).count());
+        for (int c = 0; c < qd::kNumCols; ++c) fprintf(stderr, " %.2f", up.done_ms[c]);
+        fprintf(stderr, " ms\n");
+    }
+    if (up.error.load()) throw qdcuda::CudaError{(cudaError_t)up.error.load(), "copy of the table to the device"};
     if (rc == qd::kUnsupported) return 1;
     if (rc == qd::kInvalid) { bambu_quant_set_error(err); return BAMBU_EM_EINVAL; }
     return BAMBU_EM_OK;
@@ -462,7 +553,6 @@ int bambu_quantDT(int64_t n, const int64_t *gene_code, const int64_t *txid, cons
     };
     const auto t0 = now();
     bambu_quant_pack P;
-    bambu_em_plan *plan = nullptr;
     try {
         qdcuda::CudaExec x(qdcuda::g_ws.st, qdcuda::g_ws.pool, qdcuda::g_ws.cap, qdcuda::g_ws.sms);
         qd::Result R;
@@ -482,14 +572,19 @@ int bambu_quantDT(int64_t n, const int64_t *gene_code, const int64_t *txid, cons
         const auto t1 = now();
         std::vector<double> est((size_t)std::max<int64_t>(3 * (int64_t)R.n_rows, 1));
         if (R.n_groups) {
-            rc = bambu_em_plan_create(&plan, R.n_groups, P.grp_row_ptr.data(), P.grp_col_ptr.data(), P.row_nnz_ptr.data());
+            // one cached plan: its device buffers only grow, so repeated calls allocate nothing
+            bambu_em_plan *&plan = qdcuda::g_plan;
+            rc = plan ? bambu_em_plan_reset(plan, R.n_groups, P.grp_row_ptr.data(), P.grp_col_ptr.data(), P.row_nnz_ptr.data())
+                      : bambu_em_plan_create(&plan, R.n_groups, P.grp_row_ptr.data(), P.grp_col_ptr.data(), P.row_nnz_ptr.data());
             if (!rc) rc = bambu_em_plan_bind_device(plan, R.col_idx, R.aval, R.nz_flags, R.Y, R.K, R.col_flags);
             if (!rc) rc = bambu_em_plan_run(plan, maxiter, minvalue, conv);
             if (!rc) rc = bambu_em_plan_download(plan, est.data(), nullptr, nullptr, nullptr);
-            if (rc) bambu_quant_set_error(bambu_em_last_error());
-            bambu_em_plan_destroy(plan);
-            plan = nullptr;
-            if (rc) return rc;
+            if (rc) {
+                bambu_quant_set_error(bambu_em_last_error());
+                if (plan) bambu_em_plan_destroy(plan);
+                plan = nullptr;
+                return rc;
+            }
         }
         const auto t2 = now();
         rc = bambu_quant_merge(&P, est.data(), txid_out, counts, full_length, unique_counts, n_result);
@@ -499,11 +594,9 @@ int bambu_quantDT(int64_t n, const int64_t *gene_code, const int64_t *txid, cons
                     (long long)n, ms(t0, t1), x.launches, ms(t1, t2), ms(t2, now()));
         return rc;
     } catch (const qdcuda::CudaError &e) {
-        if (plan) bambu_em_plan_destroy(plan);
         bambu_quant_set_error(std::string("CUDA error in the device packer: ") + cudaGetErrorString(e.e) + " (" + e.what + ")");
         return BAMBU_EM_ECUDA;
     } catch (const std::bad_alloc &) {
-        if (plan) bambu_em_plan_destroy(plan);
         bambu_quant_set_error("out of memory in the device packer");
         return BAMBU_EM_ENOMEM;
     }
@@ -512,4 +605,9 @@ int bambu_quantDT(int64_t n, const int64_t *gene_code, const int64_t *txid, cons
 }  // extern "C"
 
 // releases the packer's cached device workspace (bambu_em_shutdown calls it)
-void bambu_quant_release_workspace() { qdcuda::g_ws.release(); }
+void bambu_quant_release_workspace()
+{
+    if (qdcuda::g_plan) bambu_em_plan_destroy(qdcuda::g_plan);
+    qdcuda::g_plan = nullptr;
+    qdcuda::g_ws.release();
+}

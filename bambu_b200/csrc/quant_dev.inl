@@ -28,6 +28,7 @@ namespace qd {
 
 enum { kOk = 0, kUnsupported = 1, kInvalid = 2 };
 enum { kStUnsupported = 1u, kStTwoNobs = 2u, kStDupRows = 4u };
+enum { kColGene = 0, kColTx, kColEq, kColNobs, kColEqual, kColTxlen, kColRcWidth, kNumCols };
 
 struct Input {           // device pointers (equal / rcw / txl may be null)
     size_t n;
@@ -230,33 +231,18 @@ int pack(X &x, const Input &in, Result &R, std::string &err)
     uint32_t *status = x.template alloc<uint32_t>(1);
     x.fill(status, 0, 4);
 
-    // ---- validation of what the parallel formulation relies on; value ranges of the id columns ----
-    uint8_t *eqf = x.template alloc<uint8_t>(N);
-    {
-        const double nobs_limit = 9007199254740992.0 / (double)N;       // every partial sum stays exact
-        x.pfor(N, QD_LAMBDA(size_t i) {
-            const double y = nobs[i];
-            bool bad = !(y >= 0.0) || !(y <= nobs_limit) || y != (double)(int64_t)y;
-            if (d_mode && rcw) { const double w = rcw[i]; bad |= !(w >= 0.0) || !(w <= 1.7e308); }
-            if (d_mode && txl) { const double l = txl[i]; bad |= !(l > 0.0) || !(l <= 1.7e308); }
-            if (bad) qd_or(status, kStUnsupported);
-            eqf[i] = (equal && equal[i]) ? 1 : 0;
-        });
-    }
+    // The executor may still be copying the table in (column by column, in the order gene, txid, eqClassId,
+    // nobs, equal, txlen, rcWidth): x.need(c) orders the work that follows behind column c's arrival.
+    // ---- value ranges of the id columns ------------------------------------------------------------------
     int64_t mm[6];
     {
         int64_t *d_mm = x.template alloc<int64_t>(6);
-        x.minmax(gene_in, N, d_mm);
-        x.minmax(tx_in, N, d_mm + 2);
-        x.minmax(eq_in, N, d_mm + 4);
+        x.need(kColGene); x.minmax(gene_in, N, d_mm);
+        x.need(kColTx); x.minmax(tx_in, N, d_mm + 2);
+        x.need(kColEq); x.minmax(eq_in, N, d_mm + 4);
         x.d2h(mm, d_mm, 6);
     }
-    {
-        uint32_t st;
-        x.d2h(&st, status, 1);
-        if (st & kStUnsupported) return kUnsupported;
-    }
-
+    x.lap("minmax");
     // ---- simplifyNames (:236-241) + dense order-preserving codes for txid / eqClassId -----------
     uint32_t *gene = x.template alloc<uint32_t>(N), *tx = x.template alloc<uint32_t>(N), *eq = x.template alloc<uint32_t>(N);
     int64_t *tx_values = nullptr;
@@ -265,6 +251,18 @@ int pack(X &x, const Input &in, Result &R, std::string &err)
     const uint32_t NE = dense_ids(x, s, eq_in, N, mm[4], mm[5], false, eq, nullptr);
     const int b_g = qp::bits_for(G - 1), b_tx = qp::bits_for(NT - 1), b_eq = qp::bits_for(NE - 1);
 
+    x.lap("dense ids");
+    // ---- what the parallel formulation relies on: counts are non-negative integers whose sums stay exact ----
+    uint8_t *eqf = x.template alloc<uint8_t>(N);
+    {
+        const double nobs_limit = 9007199254740992.0 / (double)N;
+        x.need(kColNobs); x.need(kColEqual);
+        x.pfor(N, QD_LAMBDA(size_t i) {
+            const double y = nobs[i];
+            if (!(y >= 0.0) || !(y <= nobs_limit) || y != (double)(int64_t)y) qd_or(status, kStUnsupported);
+            eqf[i] = (equal && equal[i]) ? 1 : 0;
+        });
+    }
     // ---- (gene, eqClass) classes: id, first row; a class carries one nobs value -----------------
     uint32_t *cls = x.template alloc<uint32_t>(N);
     {
@@ -284,6 +282,7 @@ int pack(X &x, const Input &in, Result &R, std::string &err)
         });
         x.pfor(N, QD_LAMBDA(size_t j) { if (nobs[v[j]] != nobs[cls_first[run[j]]]) qd_or(status, kStTwoNobs); });
     }
+    x.lap("classes");
     // ---- (gene, tx) pairs: id, rows of each pair in table order ---------------------------------------
     uint32_t *gt = x.template alloc<uint32_t>(N), *gt_perm = x.template alloc<uint32_t>(N);
     {
@@ -305,6 +304,7 @@ int pack(X &x, const Input &in, Result &R, std::string &err)
         });
     }
 
+    x.lap("gene-tx pairs");
     // ---- per-gene sums over the distinct classes (calculateDegradationRate :247-257; K :221-228) ----
     uint8_t *cls_par = x.template alloc<uint8_t>(NC);
     double *gnobs = x.template alloc<double>(G), *gdobs = x.template alloc<double>(G);
@@ -319,6 +319,13 @@ int pack(X &x, const Input &in, Result &R, std::string &err)
     });
     double d_rate = NAN;
     if (d_mode) {
+        x.need(kColTxlen); x.need(kColRcWidth);
+        x.pfor(N, QD_LAMBDA(size_t i) {      // lengths > 0 and widths >= 0, finite
+            bool bad = false;
+            if (rcw) { const double w = rcw[i]; bad |= !(w >= 0.0) || !(w <= 1.7e308); }
+            if (txl) { const double l = txl[i]; bad |= !(l > 0.0) || !(l <= 1.7e308); }
+            if (bad) qd_or(status, kStUnsupported);
+        });
         const uint64_t neg_inf = ordered_bits(-INFINITY);
         x.pfor(G, QD_LAMBDA(size_t g) { glen[g] = neg_inf; });
         x.pfor(N, QD_LAMBDA(size_t i) { qd_max(glen + gene[i], ordered_bits(txl ? txl[i] : 1.0)); });
@@ -327,11 +334,15 @@ int pack(X &x, const Input &in, Result &R, std::string &err)
         std::vector<uint64_t> h_lenb(G);
         x.d2h(h_nb.data(), gnobs, G); x.d2h(h_db.data(), gdobs, G); x.d2h(h_par.data(), has_par, G); x.d2h(h_lenb.data(), glen, G);
         for (uint32_t g = 0; g < G; ++g) h_len[g] = from_ordered_bits(h_lenb[g]);
+        uint32_t st;
+        x.d2h(&st, status, 1);
+        if (st & kStUnsupported) return kUnsupported;
         d_rate = qp::degradation_rate(G, h_nb.data(), h_db.data(), h_par.data(), h_len.data());
         if (!(d_rate >= 0.0) || !(d_rate <= 1.7e308)) return kUnsupported;
     }
     R.d_rate = d_rate;
 
+    x.lap("gene sums + degradation rate");
     // ---- multi_align: classes with more than one distinct transcript (:276-279) -----------------------
     uint32_t *ntx = x.template alloc<uint32_t>(NC);
     x.fill(ntx, 0, 4 * (size_t)NC);
@@ -346,6 +357,7 @@ int pack(X &x, const Input &in, Result &R, std::string &err)
         x.pfor(N, QD_LAMBDA(size_t j) { if (j == 0 || k[j] != k[j - 1]) qd_inc(ntx + (uint32_t)(k[j] >> b_tx)); });
     }
 
+    x.lap("multi_align");
     // ---- per (gene, tx): nobs total (filterTxRc :333-334) and the long double sum of the partial a-values
     double *psum = x.template alloc<double>(NGT), *tsum = x.template alloc<double>(NGT);
     x.pfor(NGT, QD_LAMBDA(size_t p) {
@@ -385,6 +397,7 @@ int pack(X &x, const Input &in, Result &R, std::string &err)
         });
     }
 
+    x.lap("a-values");
     // ---- removeUnObservedGenes (:301-315): genes whose nobs are all zero; their txids in first-appearance order
     {
         const size_t mk = x.mark();
@@ -404,6 +417,7 @@ int pack(X &x, const Input &in, Result &R, std::string &err)
         }
         x.release(mk);
     }
+    x.lap("unobserved");
     // ---- initialiseOutput (:322-327): txids of the observed genes, ordered by the first appearance of their
     //      class and by table order inside it ------------------------------------------------------------
     {
@@ -431,6 +445,7 @@ int pack(X &x, const Input &in, Result &R, std::string &err)
         x.release(mk);
     }
 
+    x.lap("initialiseOutput");
     // ---- filterTxRc (:332-342): rows of observed genes whose (gene, tx) has nobs > 0 -------------------
     uint8_t *keep_gt = x.template alloc<uint8_t>(NGT);
     x.pfor(NGT, QD_LAMBDA(size_t p) { keep_gt[p] = (gnobs[gene[gt_perm[gt_start[p]]]] != 0 && tsum[p] > 0) ? 1 : 0; });
@@ -444,6 +459,7 @@ int pack(X &x, const Input &in, Result &R, std::string &err)
         uint32_t *rw = rows;
         x.pfor(N, QD_LAMBDA(size_t i) { if (fl[i]) rw[pos[i]] = (uint32_t)i; });
     }
+    x.lap("filterTxRc");
     // ---- assignGroups (:347-356): distinct txids x distinct classes per gene among the kept rows -------
     std::vector<uint32_t> h_ntx(G), h_neq(G), h_gi;
     {
@@ -467,6 +483,7 @@ int pack(X &x, const Input &in, Result &R, std::string &err)
     uint32_t *gi_of_gene = x.template alloc<uint32_t>(G);
     x.h2d(gi_of_gene, h_gi.data(), G);
 
+    x.lap("assignGroups");
     // ---- getInputList + getAMat (:359-371, 427-431) as one arena -----------------------------------------
     R.n_groups = NG;
     R.grp_row_ptr = x.template alloc<int64_t>((size_t)NG + 1);
@@ -477,8 +494,8 @@ int pack(X &x, const Input &in, Result &R, std::string &err)
         x.fill(R.row_nnz_ptr, 0, 8);
         uint32_t st;
         x.d2h(&st, status, 1);
-        if (st & kStTwoNobs) { err = "an equivalence class carries more than one nobs value"; return kInvalid; }
         if (st & kStUnsupported) return kUnsupported;
+        if (st & kStTwoNobs) { err = "an equivalence class carries more than one nobs value"; return kInvalid; }
         return kOk;
     }
     uint32_t *arow = x.template alloc<uint32_t>(N), *acol = x.template alloc<uint32_t>(N);
@@ -505,6 +522,7 @@ int pack(X &x, const Input &in, Result &R, std::string &err)
             if (j == E - 1) grp[NG] = n_arow;
         });
     }
+    x.lap("arena rows");
     // columns: unique (group, gene_sid, eqClassId) ascending
     {
         uint64_t *k = s.k;
@@ -541,6 +559,7 @@ int pack(X &x, const Input &in, Result &R, std::string &err)
             if (j == E - 1) grp[NG] = n_acol;
         });
     }
+    x.lap("arena columns");
     // entries: by (row, column)
     const int b_c = qp::bits_for(n_acol - 1);
     {
@@ -572,10 +591,11 @@ int pack(X &x, const Input &in, Result &R, std::string &err)
             if (j == E - 1) rnp[n_arow] = (int64_t)E;
         });
     }
+    x.lap("arena entries");
     uint32_t st;
     x.d2h(&st, status, 1);
-    if (st & kStTwoNobs) { err = "an equivalence class carries more than one nobs value"; return kInvalid; }
     if (st & kStUnsupported) return kUnsupported;
+    if (st & kStTwoNobs) { err = "an equivalence class carries more than one nobs value"; return kInvalid; }
     if (st & kStDupRows) { err = "duplicated (txid, gene, eqClassId) rows in readClassDt"; return kInvalid; }
     return kOk;
 }

@@ -40,6 +40,8 @@ struct HostExec {
         blocks.push_back(p);
         return static_cast<T *>(p);
     }
+    void need(int) {}
+    void lap(const char *) {}
     size_t mark() const { return 0; }
     void release(size_t) {}
     void fill(void *p, int byte, size_t bytes) { memset(p, byte, bytes); }

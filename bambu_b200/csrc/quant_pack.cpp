@@ -460,30 +460,53 @@ int bambu_quant_merge(const bambu_quant_pack *p, const double *est, int64_t *txi
     if (!p || !txid_out || !counts || !full_length || !unique_counts || !n_result) return BAMBU_EM_EINVAL;
     const size_t n_out = p->out_txid.size(), n_rows = (size_t)p->grp_row_ptr.back();
     if (n_rows && !est) return BAMBU_EM_EINVAL;
-    std::unordered_map<int64_t, uint32_t> pos;
-    pos.reserve(n_out * 2 + 16);
-    for (size_t k = 0; k < n_out; ++k) pos.emplace(p->out_txid[k], (uint32_t)k);
+    // txid -> position lookups: a direct table when the txid range is small (the usual case: txids are row
+    // numbers of the annotation), a hash map otherwise
+    int64_t lo = INT64_MAX, hi = INT64_MIN;
+    for (int64_t t : p->out_txid) { lo = std::min(lo, t); hi = std::max(hi, t); }
+    for (int64_t t : p->unobserved_txid) { lo = std::min(lo, t); hi = std::max(hi, t); }
+    const size_t n_all = n_out + p->unobserved_txid.size();
+    const bool direct = n_all && (uint64_t)hi - (uint64_t)lo < (uint64_t)(8 * n_all + (1u << 20));
+    std::vector<uint32_t> tab;
+    std::unordered_map<int64_t, uint32_t> map;
+    auto reset_index = [&]() {
+        if (direct) tab.assign((size_t)((uint64_t)hi - (uint64_t)lo) + 1, UINT32_MAX);
+        else { map.clear(); map.reserve(n_all * 2 + 16); }
+    };
+    auto find = [&](int64_t t) -> uint32_t {          // UINT32_MAX = absent
+        if (direct) return (t < lo || t > hi) ? UINT32_MAX : tab[(size_t)((uint64_t)t - (uint64_t)lo)];
+        auto it = map.find(t);
+        return it == map.end() ? UINT32_MAX : it->second;
+    };
+    auto put = [&](int64_t t, uint32_t v) {
+        if (direct) tab[(size_t)((uint64_t)t - (uint64_t)lo)] = v;
+        else map.emplace(t, v);
+    };
+    reset_index();
+    for (size_t q = 0; q < n_out; ++q) put(p->out_txid[q], (uint32_t)q);
     std::vector<double> v0(n_out, 0.0), v1(n_out, 0.0), v2(n_out, 0.0);
     for (size_t r = 0; r < n_rows; ++r) {          // arena row order = rbind order of the groups: later rows win
-        auto it = pos.find((int64_t)p->txid[r]);
-        if (it == pos.end()) continue;
-        v0[it->second] = est[r]; v1[it->second] = est[n_rows + r]; v2[it->second] = est[2 * n_rows + r];
+        const uint32_t q = find((int64_t)p->txid[r]);
+        if (q == UINT32_MAX) continue;
+        v0[q] = est[r]; v1[q] = est[n_rows + r]; v2[q] = est[2 * n_rows + r];
     }
-    std::unordered_map<int64_t, uint32_t> slot;
-    std::vector<ld> s0, s1, s2;
+    reset_index();
+    // removeDuplicates' sum(): out_txid holds every txid once and the unobserved rows are zeros, so a slot receives
+    // zeros and at most one value -- 0 + v is exact in any precision, the double accumulators below ARE R's
+    // long double sums rounded back.
     int64_t k = 0;
     auto add = [&](int64_t t, double a, double b, double c) {
-        auto it = slot.find(t);
-        if (it == slot.end()) {
-            it = slot.emplace(t, (uint32_t)k).first;
+        uint32_t q = find(t);
+        if (q == UINT32_MAX) {
+            q = (uint32_t)k;
+            put(t, q);
             txid_out[k++] = t;
-            s0.push_back(0); s1.push_back(0); s2.push_back(0);
+            counts[q] = 0.0; full_length[q] = 0.0; unique_counts[q] = 0.0;
         }
-        s0[it->second] += (ld)a; s1[it->second] += (ld)b; s2[it->second] += (ld)c;
+        counts[q] += a; full_length[q] += b; unique_counts[q] += c;
     };
     for (int64_t t : p->unobserved_txid) add(t, 0.0, 0.0, 0.0);
     for (size_t q = 0; q < n_out; ++q) add(p->out_txid[q], v0[q], v1[q], v2[q]);
-    for (int64_t q = 0; q < k; ++q) { counts[q] = (double)s0[q]; full_length[q] = (double)s1[q]; unique_counts[q] = (double)s2[q]; }
     *n_result = k;
     return BAMBU_EM_OK;
 }

@@ -33,11 +33,11 @@ inline int bits_for(uint64_t max_value)      // bits needed to hold values 0..ma
 inline double r_median(std::vector<double> x)   // median(x, na.rm = TRUE) with mean()'s long double refinement
 {
     x.erase(std::remove_if(x.begin(), x.end(), [](double v) { return std::isnan(v); }), x.end());
-    std::sort(x.begin(), x.end());
     const size_t n = x.size();
     if (!n) return NAN;
+    std::nth_element(x.begin(), x.begin() + n / 2, x.end());          // selection instead of a full sort
     if (n & 1) return x[n / 2];
-    const ld a = x[n / 2 - 1], b = x[n / 2];
+    const ld b = x[n / 2], a = *std::max_element(x.begin(), x.begin() + n / 2);
     const ld s = (a + b) / (ld)2;
     const ld t = ((a - s) + (b - s)) / (ld)2;
     return (double)(s + t);
@@ -66,23 +66,31 @@ inline std::vector<int64_t> assign_groups(const std::vector<uint32_t> &n_tx, con
                                           std::vector<uint32_t> &group_index)
 {
     const size_t G = n_tx.size();
-    std::vector<uint32_t> genes;
-    for (uint32_t g = 0; g < G; ++g) if (n_tx[g]) genes.push_back(g);
-    std::vector<int64_t> grp_of_gene(G, 0);
-    std::vector<uint64_t> dim(genes.size());
-    for (size_t k = 0; k < genes.size(); ++k) dim[k] = (uint64_t)n_tx[genes[k]] * n_eq[genes[k]];
-    std::vector<uint32_t> order(genes.size());
-    for (size_t k = 0; k < order.size(); ++k) order[k] = (uint32_t)k;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return dim[a] < dim[b]; });
-    uint64_t cum = 0;
-    for (uint32_t k : order) { cum += dim[k]; grp_of_gene[genes[k]] = (int64_t)(cum / 1000 + 1); }
+    struct DG { uint64_t dim; uint32_t gene; };
+    std::vector<DG> a, b;
+    a.reserve(G);
+    uint64_t dmax = 0;
+    for (uint32_t g = 0; g < G; ++g)
+        if (n_tx[g]) { a.push_back(DG{(uint64_t)n_tx[g] * n_eq[g], g}); dmax = std::max(dmax, a.back().dim); }
+    // order(tr_dimension): stable LSD radix on the dimension (genes enter in ascending gene_sid)
+    b.resize(a.size());
+    for (int sh = 0; sh < bits_for(dmax); sh += 16) {
+        std::vector<uint32_t> cnt(65537, 0);
+        for (const DG &e : a) ++cnt[((e.dim >> sh) & 0xffffu) + 1];
+        for (int d = 0; d < 65536; ++d) cnt[d + 1] += cnt[d];
+        for (const DG &e : a) b[cnt[(e.dim >> sh) & 0xffffu]++] = e;
+        a.swap(b);
+    }
+    // the cumulative sum only grows, so the group ids come out sorted: number them as they appear
     std::vector<int64_t> gids;
-    for (uint32_t g : genes) gids.push_back(grp_of_gene[g]);
-    std::sort(gids.begin(), gids.end());
-    gids.erase(std::unique(gids.begin(), gids.end()), gids.end());
     group_index.assign(G, 0);
-    for (uint32_t g : genes)
-        group_index[g] = (uint32_t)(std::lower_bound(gids.begin(), gids.end(), grp_of_gene[g]) - gids.begin());
+    uint64_t cum = 0;
+    for (const DG &e : a) {
+        cum += e.dim;
+        const int64_t id = (int64_t)(cum / 1000 + 1);
+        if (gids.empty() || gids.back() != id) gids.push_back(id);
+        group_index[e.gene] = (uint32_t)(gids.size() - 1);
+    }
     return gids;
 }
 

@@ -274,7 +274,7 @@ def _gene_codes(gid):
     """Any integer coding of GENEID (the native packer numbers genes by first appearance itself)."""
     gid = np.asarray(gid)
     if gid.dtype.kind in "iu":
-        return gid.astype(np.int64)
+        return gid.astype(np.int64, copy=False)
     return np.unique(gid, return_inverse=True)[1].astype(np.int64)
 
 

@@ -112,6 +112,11 @@ int bambu_em_plan_create(bambu_em_plan **plan, int64_t n_groups,
                          const int64_t *grp_row_ptr, const int64_t *grp_col_ptr,
                          const int64_t *row_nnz_ptr);
 int bambu_em_plan_destroy(bambu_em_plan *plan);
+/* Re-analyse a NEW group structure in an existing plan, keeping its device memory (buffers only grow): the
+ * cheap way to push differently shaped arenas (one per sample) through one plan.  The payload has to be
+ * uploaded / bound again. */
+int bambu_em_plan_reset(bambu_em_plan *plan, int64_t n_groups, const int64_t *grp_row_ptr,
+                        const int64_t *grp_col_ptr, const int64_t *row_nnz_ptr);
 /* stream all work of this plan is ordered on (a cudaStream_t passed as void*);
  * NULL = the plan's own stream.  Lets a harness bracket runs with its own events. */
 int bambu_em_plan_set_stream(bambu_em_plan *plan, void *cuda_stream);
