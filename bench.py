@@ -167,6 +167,32 @@ def workload_config(args, n):
 
 
 # ----------------------------------------------------------------------------- B200 arm
+def quantdt_stage(args):
+    """Latency of the whole per-sample stage (bambu.quantDT, R/bambu-quantify.R:53-74) on ONE config-2 sample given as
+    the long table: bambu_quantDT (table H2D, device pack, EM on the arena in HBM, merge by txid) next to the same
+    call with the host packer.  An extra object in the JSON line; not part of `value` / `e2e`."""
+    from bambu_b200 import quantify as Q, synthetic
+    ann = synthetic.annotation_for("config2", scale=args.scale)
+    tab = synthetic.sample_arena(ann, 0, long_table=True)
+
+    def best(reps, **kw):
+        ts = []
+        for _ in range(reps):
+            t = time.perf_counter()
+            out = Q.bambu_quantDT_native(tab, **kw)
+            ts.append(time.perf_counter() - t)
+        return min(ts) * 1e3, float(np.median(ts)) * 1e3, out
+
+    Q.bambu_quantDT_native(tab)
+    dev_best, dev_med, out = best(5)
+    host_best, host_med, out_h = best(2, host_pack=True)
+    same = bool(np.array_equal(out["txid"], out_h["txid"]) and out["counts"].tobytes() == out_h["counts"].tobytes())
+    return {"rows": int(len(tab["txid"])), "transcripts": int(len(out["txid"])), "ms": dev_med, "ms_best": dev_best,
+            "ms_host_packer": host_med, "identical_to_host_packer": same,
+            "what": "python call of bambu_quantDT on one config-2 sample (long table in pageable host memory -> "
+                    "counts by txid), median of 5; ms_host_packer = the same with csrc/quant_pack.cpp in front"}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -328,6 +354,8 @@ def run_b200(args):
                 "note": "B1: dense literal restatement of src/em.cpp incl. theta_trace, groups over all cores (OpenMP)",
                 "sparse_value": w2 * 3 / s2,
                 "sparse_note": "B2: same arithmetic on the non-zeros only (CSR/CSC), all cores"}
+        if world == 1 and not args.no_stage:
+            line["quantDT_stage"] = quantdt_stage(args)
         print(json.dumps(line))
     plan.close()
     if world > 1:
@@ -345,6 +373,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every sample (debugging)")
     ap.add_argument("--cpu-frac", type=float, default=8.0, help="CPU arms run on 1/cpu-frac of one sample's groups")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-stage", action="store_true", help="skip the quantDT_stage latency measurement")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
