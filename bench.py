@@ -371,7 +371,7 @@ def main():
     ap.add_argument("--samples", type=int, default=int(os.environ.get("BAMBU_BENCH_SAMPLES", "100")),
                     help="cohort samples per GPU")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every sample (debugging)")
-    ap.add_argument("--cpu-frac", type=float, default=8.0, help="CPU arms run on 1/cpu-frac of one sample's groups")
+    ap.add_argument("--cpu-frac", type=float, default=1.0, help="CPU arms run on 1/cpu-frac of one sample's groups")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stage", action="store_true", help="skip the quantDT_stage latency measurement")
     args = ap.parse_args()

@@ -129,13 +129,44 @@ def chr9_e2e():
     }
 
 
+def gene_level():
+    """Inputs and expected outputs of tests/testthat/test_transcriptToGeneExpression.R:3-28: the four stored
+    bambu outputs of inst/extdata and the se*GeneExpected objects of R/sysdata.rda (data-raw/DATASET.R:92-102)."""
+    import sys as _sys
+    _sys.setrecursionlimit(100000)
+    objs = dict(read_rda(os.path.join(REF, "R/sysdata.rda"), 13))
+    cases = []
+    for fname, key in (("seOutput_%s.rds", "seGeneExpected"), ("seOutputExtended_%s.rds", "seExtendedGeneExpected"),
+                       ("seOutputCombined_%s.rds", "seCombinedGeneExpected"),
+                       ("seOutputCombinedExtended_%s.rds", "seCombinedExtendedGeneExpected")):
+        se = read_rds(os.path.join(REF, "inst/extdata", fname % STEM))
+        ld = se.attrs["assays"].attrs["data"].attrs["listData"]
+        counts = ld["counts"]
+        em = se.attrs["rowRanges"].attrs["elementMetadata"].attrs["listData"]
+        inc = se.attrs["metadata"]["incompatibleCounts"]
+        exp = objs[key]
+        eld = exp.attrs["assays"].attrs["data"].attrs["listData"]
+        dn = eld["counts"].attrs["dimnames"].value
+        cases.append({
+            "name": key, "source": fname % STEM,
+            "input": {"counts": _nan_to_none(counts.value), "dim": counts.attrs["dim"].value,
+                      "TXNAME": em["TXNAME"].value, "GENEID": em["GENEID"].value,
+                      "sample_names": se.attrs["colData"].attrs["rownames"].value,
+                      "incompatibleCounts": {n: inc[n].value for n in inc.names()}},
+            "expected": {"GENEID": dn[0].value, "sample_names": dn[1].value, "dim": eld["counts"].attrs["dim"].value,
+                         "counts": _nan_to_none(eld["counts"].value), "CPM": _nan_to_none(eld["CPM"].value)}})
+    return {"cases": cases}
+
+
 def main():
     with open(os.path.join(HERE, "quantDT_unit.json"), "w") as f:
         json.dump(unit_goldens(), f, indent=1)
     sys.setrecursionlimit(20000)
     with open(os.path.join(HERE, "chr9_e2e.json"), "w") as f:
         json.dump(chr9_e2e(), f)
-    print("wrote quantDT_unit.json, chr9_e2e.json")
+    with open(os.path.join(HERE, "gene_level.json"), "w") as f:
+        json.dump(gene_level(), f)
+    print("wrote quantDT_unit.json, chr9_e2e.json, gene_level.json")
 
 
 if __name__ == "__main__":

@@ -88,20 +88,20 @@ class Reader:
         has_attr = bool(flags & 0x200)
         has_tag = bool(flags & 0x400)
 
-        if t == 254:  # NILVALUE
+        if t == 254:  # NILVALUE_SXP
             return None
-        if t == 253:  # R_EmptyEnv
-            return RObj("env", "empty")
-        if t == 252:  # base env
-            return RObj("env", "base")
-        if t == 251:  # missing arg
-            return RObj("missing")
-        if t == 250:  # unbound
-            return RObj("unbound")
-        if t == 249:
-            return RObj("env", "basenamespace")
-        if t == 248:
+        if t == 253:  # GLOBALENV_SXP
             return RObj("env", "global")
+        if t == 252:  # UNBOUNDVALUE_SXP
+            return RObj("unbound")
+        if t == 251:  # MISSINGARG_SXP
+            return RObj("missing")
+        if t == 250:  # BASENAMESPACE_SXP
+            return RObj("env", "basenamespace")
+        if t == 242:  # EMPTYENV_SXP
+            return RObj("env", "empty")
+        if t == 241:  # BASEENV_SXP
+            return RObj("env", "base")
         if t == 255:  # reference
             idx = flags >> 8
             if idx == 0:
@@ -111,7 +111,7 @@ class Reader:
             name = self.item()
             self.refs.append(name)
             return name
-        if t == 247 or t == 246:  # namespace / package spec
+        if t in (249, 248, 247):  # NAMESPACESXP / PACKAGESXP / PERSISTSXP: a string vector, entered in the ref table
             self.i32()
             n = self.i32()
             info = [self.item() for _ in range(n)]
@@ -212,8 +212,20 @@ class Reader:
             self.p += n
         elif t == 25:  # S4
             o = RObj("S4")
-        elif t == 21:  # byte code: not needed for the fixtures
-            raise NotImplementedError("byte code")
+        elif t == 21:  # byte code (ReadBC in R's serialize.c): parsed only to stay aligned
+            nreps = self.i32()
+            reps = [None] * nreps
+            o = RObj("bytecode", self._bc1(reps))
+        elif t in (7, 8):  # special / builtin: a name
+            n = self.i32()
+            o = RObj("builtin", self.b[self.p:self.p + n].decode())
+            self.p += n
+        elif t == 15:  # complex
+            n = self.length()
+            o = RObj("complex", self.f64s(2 * n))
+        elif t == 23:  # weak reference
+            o = RObj("weakref")
+            self.refs.append(o)
         else:
             raise NotImplementedError("SEXPTYPE %d at offset %d" % (t, self.p))
         if has_attr:
@@ -221,6 +233,41 @@ class Reader:
             if a:
                 o.attrs = self._attrs_to_dict(a)
         return o
+
+    # -- byte code ------------------------------------------------------------
+    def _bc1(self, reps):
+        code = self.item()
+        n = self.i32()
+        consts = []
+        for _ in range(n):
+            t = self.i32()
+            if t == 21:
+                consts.append(self._bc1(reps))
+            elif t in (6, 2, 244, 243, 240, 239):
+                consts.append(self._bclang(t, reps))
+            else:
+                consts.append(self.item())
+        return (code, consts)
+
+    def _bclang(self, t, reps):
+        if t == 243:  # BCREPREF
+            return reps[self.i32()]
+        if t in (244, 6, 2, 240, 239):
+            pos = -1
+            if t == 244:  # BCREPDEF
+                pos = self.i32()
+                t = self.i32()
+            hasattr_ = t in (240, 239)
+            o = RObj("bclang", None)
+            if pos >= 0:
+                reps[pos] = o
+            attr = self.item() if hasattr_ else None
+            tag = self.item()
+            car = self._bclang(self.i32(), reps)
+            cdr = self._bclang(self.i32(), reps)
+            o.value = (attr, tag, car, cdr)
+            return o
+        return self.item()
 
     @staticmethod
     def _attrs_to_dict(a: RObj) -> dict:

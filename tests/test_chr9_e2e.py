@@ -2,7 +2,8 @@
 replayed without R from the objects stored in inst/extdata/seOutput_distTable_*.rds and
 seReadClassUnstranded_*.rds (tests/golden/chr9_e2e.json; tests/testthat/test_bambu_arguments.R:33-43
 and test_quant.R:57-66 compare the same four assays).  genEquiRCs and the tail of bambu.quantify
-are restated in oracle/equirc_ref.py; bambu.quantDT is the product's host mirror."""
+is restated in oracle/equirc_ref.py; bambu.quantDT and the tail of bambu.quantify (bambu_b200/assays.py) are the
+product's host mirror."""
 import json
 import os
 
@@ -19,13 +20,15 @@ def fx():
 
 
 def _run(fx, em):
-    from oracle.equirc_ref import assemble_assays, gen_equi_rcs
-    from bambu_b200.quantify import bambu_quantDT, calculateCPM
+    from oracle.equirc_ref import gen_equi_rcs
+    from bambu_b200.assays import quantify_assays
+    from bambu_b200.quantify import bambu_quantDT
     tab = gen_equi_rcs(fx)
     assert len(tab["txid"]) == 491 and len(set(tab["eqClassId"])) == 222
     det = {}
     quant = bambu_quantDT(tab, {"degradationBias": True}, em=em, details=det)
-    return assemble_assays(fx, quant, calculateCPM), det
+    inc = [np.nan if v is None else v for v in fx["incompatibleCounts"]["counts"]]
+    return quantify_assays(quant, fx["annotation"]["txid"], inc), det
 
 
 def _check(fx, assays, det):
