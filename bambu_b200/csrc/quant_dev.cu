@@ -602,6 +602,41 @@ int bambu_quantDT(int64_t n, const int64_t *gene_code, const int64_t *txid, cons
     }
 }
 
+// bambu_quantDT for R's .C() interface, which needs no compiled shim: every argument is a pointer to one of R's
+// own vector types (integer = int, numeric = double, logical = int), scalars are length-1 vectors, the return code
+// travels in the last argument.  dyn.load("libbambu_em.so"); .C("bambu_quantDT_dotC", ...) -- see INTEGRATION.md.
+void bambu_quantDT_dotC(const int *n_rows, const int *gene_code, const int *txid, const int *eqClassId, const double *nobs,
+                        const int *equal, const double *rcWidth, const double *txlen, const int *degradation_bias,
+                        const int *maxiter, const double *minvalue, const double *conv, int *txid_out, double *counts,
+                        double *full_length, double *unique_counts, int *n_result, double *d_rate, int *rc)
+{
+    if (!rc) return;
+    if (!n_rows || !degradation_bias || !maxiter || !minvalue || !conv || !n_result || *n_rows < 0) {
+        bambu_quant_set_error("NULL or negative scalar argument");
+        *rc = BAMBU_EM_EINVAL;
+        return;
+    }
+    const size_t N = (size_t)*n_rows;
+    try {
+        std::vector<int64_t> g(N), t(N), e(N), t_out(std::max<size_t>(N, 1));
+        std::vector<uint8_t> eqf(N);
+        if (N && (!gene_code || !txid || !eqClassId)) { bambu_quant_set_error("Columns GENEID, txid, eqClassId, nobs, are missing from object."); *rc = BAMBU_EM_EINVAL; return; }
+        for (size_t i = 0; i < N; ++i) { g[i] = gene_code[i]; t[i] = txid[i]; e[i] = eqClassId[i]; }
+        if (equal) for (size_t i = 0; i < N; ++i) eqf[i] = equal[i] == 1;       // NA_LOGICAL (INT_MIN) counts as FALSE
+        int64_t k = 0;
+        *rc = bambu_quantDT((int64_t)N, g.data(), t.data(), e.data(), nobs, equal ? eqf.data() : nullptr, rcWidth, txlen,
+                            *degradation_bias, *maxiter, *minvalue, *conv, t_out.data(), counts, full_length, unique_counts,
+                            &k, d_rate);
+        if (*rc == BAMBU_EM_OK) {
+            if (txid_out) for (int64_t q = 0; q < k; ++q) txid_out[q] = (int)t_out[(size_t)q];
+            *n_result = (int)k;
+        }
+    } catch (const std::bad_alloc &) {
+        bambu_quant_set_error("out of memory");
+        *rc = BAMBU_EM_ENOMEM;
+    }
+}
+
 }  // extern "C"
 
 // releases the packer's cached device workspace (bambu_em_shutdown calls it)

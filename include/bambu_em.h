@@ -193,6 +193,14 @@ int bambu_quantDT_hostpack(int64_t n_rows, const int64_t *gene_code, const int64
                   const double *nobs, const uint8_t *equal, const double *rcWidth, const double *txlen,
                   int32_t degradation_bias, int32_t maxiter, double minvalue, double conv, int64_t *txid_out,
                   double *counts, double *full_length, double *unique_counts, int64_t *n_result, double *d_rate);
+/* bambu_quantDT for R's .C() interface (no compiled shim needed): every argument points to one of R's own vector
+ * types -- integer (int), numeric (double), logical (int; TRUE = 1) -- scalars are length-1 vectors, and the return
+ * code comes back through rc.  Output vectors must hold as many elements as there are distinct txids (<= n_rows). */
+void bambu_quantDT_dotC(const int *n_rows, const int *gene_code, const int *txid, const int *eqClassId,
+                        const double *nobs, const int *equal, const double *rcWidth, const double *txlen,
+                        const int *degradation_bias, const int *maxiter, const double *minvalue, const double *conv,
+                        int *txid_out, double *counts, double *full_length, double *unique_counts, int *n_result,
+                        double *d_rate, int *rc);
 /* bambu_quant_pack_create done by the GPU (csrc/quant_dev.cu), the arena copied back into a host pack object.
  * used_device (may be NULL) receives 1, or 0 when the table went through the host packer (see above). */
 int bambu_quant_pack_create_gpu(bambu_quant_pack **pack, int64_t n_rows, const int64_t *gene_code, const int64_t *txid,

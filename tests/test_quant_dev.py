@@ -252,3 +252,33 @@ def test_gpu_quantDT_goldens(built, unit_goldens):
             assert got["txid"].tolist() == [int(t) for t in exp["txid"]]
             for name in ("counts", "fullLengthCounts", "uniqueCounts"):
                 assert_same_doubles(got[name], np.array(exp[name]), f"{case['name']} {name}")
+
+
+@pytest.mark.gpu
+def test_dotC_entry_point(built, unit_goldens):
+    """bambu_quantDT_dotC (R's .C() calling convention: int / double / logical-as-int vectors, rc by pointer)
+    returns the goldens of tests/testthat/test_quant.R:12-27."""
+    from bambu_b200 import _lib
+    L = _lib.lib()
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)      # noqa: E731
+    i32 = lambda v: np.array([v], dtype=np.int32)          # noqa: E731
+    f64 = lambda v: np.array([v], dtype=np.float64)        # noqa: E731
+    par = unit_goldens["emParameters"]
+    for case in unit_goldens["cases"]:
+        tab = case["input"]
+        n = len(tab["txid"])
+        cols = [Q._gene_codes(tab["GENEID"]).astype(np.int32), np.asarray(tab["txid"], np.int32), np.asarray(tab["eqClassId"], np.int32),
+                np.asarray(tab["nobs"], np.float64), np.asarray(tab["equal"], bool).astype(np.int32),
+                np.asarray(tab["rcWidth"], np.float64), np.asarray(tab["txlen"], np.float64)]
+        t_out, c0, c1, c2 = np.zeros(n, np.int32), np.zeros(n), np.zeros(n), np.zeros(n)
+        k, d, rc = i32(0), f64(0), i32(-99)
+        L.bambu_quantDT_dotC(ptr(i32(n)), *[ptr(c) for c in cols], ptr(i32(1)), ptr(i32(par["maxiter"])),
+                             ptr(f64(par["minvalue"])), ptr(f64(par["conv"])), ptr(t_out), ptr(c0), ptr(c1), ptr(c2), ptr(k),
+                             ptr(d), ptr(rc))
+        assert rc[0] == 0
+        exp = case["expected"]["estOutput_wBC"]
+        m = int(k[0])
+        assert t_out[:m].tolist() == [int(t) for t in exp["txid"]]
+        assert_same_doubles(c0[:m], np.array(exp["counts"]), "counts")
+        assert_same_doubles(c1[:m], np.array(exp["fullLengthCounts"]), "fullLengthCounts")
+        assert_same_doubles(c2[:m], np.array(exp["uniqueCounts"]), "uniqueCounts")
