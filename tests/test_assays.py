@@ -89,3 +89,29 @@ def test_r_round():
     x = np.array([0.5, 1.5, 2.5, 0.125, 0.375])
     assert A.r_round(x, 0).tolist() == [0.0, 2.0, 2.0, 0.0, 0.0]
     assert A.r_round(x, 2).tolist() == [0.5, 1.5, 2.5, 0.12, 0.38]
+
+
+def test_genEquiRCs_chr9(oracle_mod):
+    """The product's genEquiRCs (bambu_b200/equirc.py) on the bundled run: the same long table as the loop-level
+    restatement (oracle/equirc_ref.py; 491 rows, 222 classes -- SURVEY 8c), and through bambu.quantDT and
+    quantify_assays the four assays the reference stores (tests/testthat/test_bambu_arguments.R:33-43)."""
+    from oracle.equirc_ref import gen_equi_rcs
+    from bambu_b200.equirc import AnnotationClasses, genEquiRCs
+    from bambu_b200.quantify import bambu_quantDT
+    with open(os.path.join(GOLDEN, "chr9_e2e.json")) as f:
+        fx = json.load(f)
+    ann = AnnotationClasses(fx["annotation"])
+    tab = genEquiRCs(fx["distTable"], fx["readClasses"], ann)
+    ref = gen_equi_rcs(fx)
+    assert len(tab["txid"]) == 491 and len(set(tab["eqClassId"].tolist())) == 222
+    for col in ("GENEID", "txid", "eqClassId", "nobs", "equal", "rcWidth", "txlen", "minRC"):
+        assert list(tab[col]) == list(ref[col]), col
+    again = genEquiRCs(fx["distTable"], fx["readClasses"], ann)          # the cached annotation side is not consumed
+    assert again["eqClassId"].tolist() == tab["eqClassId"].tolist()
+    quant = bambu_quantDT(tab, {"degradationBias": True},
+                          em=lambda a, maxiter, conv, minvalue: oracle_mod.em_batched(a, maxiter=maxiter, conv=conv,
+                                                                                      minvalue=minvalue))
+    inc = [np.nan if v is None else v for v in fx["incompatibleCounts"]["counts"]]
+    got = A.quantify_assays(quant, fx["annotation"]["txid"], inc)
+    for name in ("counts", "CPM", "fullLengthCounts", "uniqueCounts"):
+        assert_same_doubles(got[name], np.array(fx["expected_assays"][name], dtype=np.float64), name)

@@ -1,9 +1,10 @@
 """BASELINE.json configs[0]: the reference's bundled chr9:1-1Mb run (SGNex A549 directRNA),
 replayed without R from the objects stored in inst/extdata/seOutput_distTable_*.rds and
 seReadClassUnstranded_*.rds (tests/golden/chr9_e2e.json; tests/testthat/test_bambu_arguments.R:33-43
-and test_quant.R:57-66 compare the same four assays).  genEquiRCs and the tail of bambu.quantify
-is restated in oracle/equirc_ref.py; bambu.quantDT and the tail of bambu.quantify (bambu_b200/assays.py) are the
-product's host mirror."""
+and test_quant.R:57-66 compare the same four assays).  The whole chain is product code -- genEquiRCs
+(bambu_b200/equirc.py), bambu.quantDT (quantify.py + the EM), the tail of bambu.quantify (assays.py); only the EM
+callable changes between the CPU run (oracle) and the -m gpu run (libbambu_em.so).  oracle/equirc_ref.py keeps an
+independent loop-level restatement of genEquiRCs."""
 import json
 import os
 
@@ -20,10 +21,10 @@ def fx():
 
 
 def _run(fx, em):
-    from oracle.equirc_ref import gen_equi_rcs
     from bambu_b200.assays import quantify_assays
+    from bambu_b200.equirc import genEquiRCs
     from bambu_b200.quantify import bambu_quantDT
-    tab = gen_equi_rcs(fx)
+    tab = genEquiRCs(fx["distTable"], fx["readClasses"], fx["annotation"])
     assert len(tab["txid"]) == 491 and len(set(tab["eqClassId"])) == 222
     det = {}
     quant = bambu_quantDT(tab, {"degradationBias": True}, em=em, details=det)
