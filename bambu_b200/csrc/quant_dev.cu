@@ -407,6 +407,8 @@ int run_device_pack(qdcuda::CudaExec &x, int64_t n, const int64_t *gene, const i
     qd::Input in;
     in.n = N;
     in.d_mode = d_mode;
+    if (getenv("BAMBU_PACK_POISON"))      // debugging aid: nothing may depend on what the workspace held before
+        QD_CUDA(cudaMemsetAsync(x.pool, 0xA5, x.cap, x.st));
     qdcuda::Uploader up;
     for (int c = 0; c < qd::kNumCols; ++c) up.st[c] = qdcuda::g_ws.up_st[c];
     QD_CUDA(cudaGetDevice(&up.device));
