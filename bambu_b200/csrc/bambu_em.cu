@@ -1045,12 +1045,15 @@ static int batched_impl(int64_t n_groups, const int64_t *grp_row_ptr, const int6
     TRY(ensure_device());
     g_pipe_used = true;
     const int64_t total_rows = grp_row_ptr[n_groups];
-    const int64_t target = chunk_target_bytes();
+    const int64_t target_max = chunk_target_bytes();
     int rc = BAMBU_EM_OK;
     int64_t g0 = 0;
     int k = 0;
     while (g0 < n_groups && !rc) {
-        // next chunk: groups until ~target bytes of arena
+        // next chunk: groups until ~target bytes of arena.  The first chunks are small (32 MB, doubling) so the
+        // GPU starts after a short copy; later ones are large enough to amortise the per-chunk host work.
+        const int64_t ramp = (int64_t)32 << (20 + (k < 6 ? k : 6));
+        const int64_t target = ramp < target_max ? ramp : target_max;
         int64_t g1 = g0;
         int64_t bytes = 0;
         while (g1 < n_groups && (g1 == g0 || bytes < target)) {
