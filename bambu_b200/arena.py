@@ -171,6 +171,32 @@ class Arena:
                      np.concatenate((z, np.cumsum(rl))), self.col_idx[ent], self.aval[ent], self.nz_flags[ent],
                      self.Y[cols], self.K[cols], self.col_flags[cols], self.txid[rows])
 
+    # ------------------------------------------------------------ on disk
+    FORMAT = "bambu-arena-1"
+
+    def save(self, path) -> None:
+        """Write the arena as an uncompressed ``.npz`` (one member per ABI array, plus ``sample_grp_ptr`` and a
+        format tag): a cohort packed once can be re-quantified later without R."""
+        members = {n: np.ascontiguousarray(getattr(self, n)) for n in
+                   ("grp_row_ptr", "grp_col_ptr", "row_nnz_ptr", "col_idx", "aval", "nz_flags", "Y", "K", "col_flags", "txid")}
+        if self.sample_grp_ptr is not None:
+            members["sample_grp_ptr"] = np.asarray(self.sample_grp_ptr, dtype=np.int64)
+        members["format"] = np.array(self.FORMAT)
+        with open(path, "wb") as f:
+            np.savez(f, **members)
+
+    @staticmethod
+    def load(path, validate: bool = True) -> "Arena":
+        with np.load(path, allow_pickle=False) as z:
+            if "format" not in z.files or str(z["format"]) != Arena.FORMAT:
+                raise ValueError(f"{path}: not a {Arena.FORMAT} file")
+            a = Arena(z["grp_row_ptr"], z["grp_col_ptr"], z["row_nnz_ptr"], z["col_idx"], z["aval"], z["nz_flags"], z["Y"],
+                      z["K"], z["col_flags"], z["txid"],
+                      sample_grp_ptr=z["sample_grp_ptr"] if "sample_grp_ptr" in z.files else None)
+        if validate:
+            a.validate()
+        return a
+
     @staticmethod
     def from_dense_groups(groups) -> "Arena":
         """Build an arena from dense per-group inputs, each a tuple

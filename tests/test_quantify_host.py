@@ -98,3 +98,19 @@ def test_missing_columns_error():
 def test_calculateCPM():
     c = np.array([10.0, 30.0, 0.0])
     assert np.allclose(Q.calculateCPM(c, [60.0]), c / 100 * 1e6)
+
+
+def test_arena_file_round_trip(tmp_path):
+    from bambu_b200 import synthetic
+    from bambu_b200.arena import Arena
+    a = Arena.concatenate([synthetic.config2(scale=0.004), synthetic.config2(seed=5, scale=0.004)])
+    p = tmp_path / "cohort.arena.npz"
+    a.save(p)
+    b = Arena.load(p)
+    for name in ("grp_row_ptr", "grp_col_ptr", "row_nnz_ptr", "col_idx", "aval", "nz_flags", "Y", "K", "col_flags", "txid",
+                 "sample_grp_ptr"):
+        x, y = getattr(a, name), getattr(b, name)
+        assert x.dtype == y.dtype and x.tobytes() == y.tobytes(), name
+    np.savez(tmp_path / "other.npz", x=np.zeros(3))
+    with pytest.raises(ValueError, match="not a bambu-arena-1"):
+        Arena.load(tmp_path / "other.npz")
