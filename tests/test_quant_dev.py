@@ -282,3 +282,63 @@ def test_dotC_entry_point(built, unit_goldens):
         assert_same_doubles(c0[:m], np.array(exp["counts"]), "counts")
         assert_same_doubles(c1[:m], np.array(exp["fullLengthCounts"]), "fullLengthCounts")
         assert_same_doubles(c2[:m], np.array(exp["uniqueCounts"]), "uniqueCounts")
+
+
+def _table_with_giant_gene(rng, n_small=150, m_giant=2500, n_cls_giant=30000):
+    """random small genes + one locus with thousands of transcripts and classes (long (gene, tx) runs in the
+    packer, a streamed-tier group in the EM)."""
+    tab = random_long_table(rng, n_genes=n_small, shared_tx=False)
+    tx0 = max(tab["txid"]) + 1
+    cls0 = max(tab["eqClassId"]) + 1
+    k = 1 + rng.binomial(m_giant - 1, 12.0 / m_giant, n_cls_giant)
+    cls = np.repeat(np.arange(n_cls_giant), k)
+    member = np.concatenate([rng.choice(m_giant, size=int(kk), replace=False) for kk in k])
+    nobs_c = np.where(rng.random(n_cls_giant) < 0.4, 1.0 + rng.negative_binomial(0.5, 0.5 / 40.5, n_cls_giant), 0.0)
+    eq_pick = rng.random(len(cls)) < 0.08
+    first = np.ones(len(cls), bool)
+    first[1:] = cls[1:] != cls[:-1]
+    equal = eq_pick & first                                   # at most one full-length member per class
+    w_c = rng.integers(1, 3000, n_cls_giant).astype(float)
+    txlen = rng.integers(400, 6000, m_giant).astype(float)
+    # every transcript also gets its own single-member class so that it keeps an observation
+    u_nobs = 1.0 + rng.negative_binomial(0.5, 0.5 / 40.5, m_giant)
+    out = {kname: list(v) for kname, v in tab.items()}
+    out["GENEID"] += ["GIANT"] * (len(cls) + m_giant)
+    out["txid"] += (tx0 + member).tolist() + (tx0 + np.arange(m_giant)).tolist()
+    out["eqClassId"] += (cls0 + cls).tolist() + (cls0 + n_cls_giant + np.arange(m_giant)).tolist()
+    out["nobs"] += nobs_c[cls].tolist() + u_nobs.tolist()
+    out["equal"] += equal.tolist() + [True] * m_giant
+    out["rcWidth"] += w_c[cls].tolist() + txlen.tolist()
+    out["txlen"] += txlen[member].tolist() + txlen.tolist()
+    perm = rng.permutation(len(out["txid"]))
+    return {kname: [v[i] for i in perm] for kname, v in out.items()}
+
+
+@pytest.mark.gpu
+def test_gpu_quantDT_with_giant_gene(built):
+    rng = np.random.default_rng(20260003)
+    tab = _table_with_giant_gene(rng)
+    a = Q.pack_quantDT_native(tab, gpu=True)
+    assert a.used_device
+    b = Q.pack_quantDT_native(tab)
+    same_pack(a, b)
+    M, N, _ = b.arena.group_shapes()
+    assert M.max() >= 2500 and N.max() >= 30000
+    got = Q.bambu_quantDT_native(tab)
+    want = Q.bambu_quantDT_native(tab, host_pack=True)
+    assert np.array_equal(got["txid"], want["txid"])
+    for name in ("counts", "fullLengthCounts", "uniqueCounts"):
+        assert_same_doubles(got[name], want[name], name)
+    # mass conservation inside the giant locus: every observed read is assigned to one of its transcripts
+    # (the small random genes may hold zero-width classes, whose NaN handling the parity above already covers)
+    seen, total = set(), 0.0
+    giant_tx = set()
+    for g, c, n, t in zip(tab["GENEID"], tab["eqClassId"], tab["nobs"], tab["txid"]):
+        if g != "GIANT":
+            continue
+        giant_tx.add(t)
+        if c not in seen:
+            seen.add(c)
+            total += n
+    mass = got["counts"][np.isin(got["txid"], np.array(sorted(giant_tx)))].sum()
+    assert np.isfinite(mass) and abs(mass - total) <= 1e-6 * total
