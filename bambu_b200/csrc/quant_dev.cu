@@ -9,6 +9,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <new>
 #include <algorithm>
 #include <atomic>
@@ -233,6 +234,7 @@ struct Uploader {
 struct CudaExec {
     Uploader *up = nullptr;
     bool have[qd::kNumCols] = {};
+    std::function<void()> on_arrival[qd::kNumCols];      // e.g. widening of an int32 column, queued behind its copy
     cudaStream_t st = nullptr;
     uint8_t *pool = nullptr;
     size_t cap = 0, top = 0;
@@ -258,6 +260,7 @@ struct CudaExec {
         if (up->error.load()) throw CudaError{(cudaError_t)up->error.load(), "copy of the table to the device"};
         QD_CUDA(cudaStreamWaitEvent(st, up->ev[c], 0));
         have[c] = true;
+        if (on_arrival[c]) on_arrival[c]();
     }
     // BAMBU_PACK_TIMING: wall time of each stage of the pipeline (drains the stream, so it perturbs the total)
     bool timing = false;
@@ -399,8 +402,10 @@ struct DevTable {          // the long table in device memory
 };
 
 // copies the table into the workspace and runs the pipeline.  Returns BAMBU_EM_* or +1 for "use the host packer".
-int run_device_pack(qdcuda::CudaExec &x, int64_t n, const int64_t *gene, const int64_t *tx, const int64_t *eq,
-                    const double *nobs, const uint8_t *equal, const double *rcw, const double *txl, bool d_mode,
+// IdT: int64_t, or int (R's integer): copied as they are and widened on the device.  EqT: uint8_t, or int (R's logical).
+template <class IdT, class EqT>
+int run_device_pack(qdcuda::CudaExec &x, int64_t n, const IdT *gene, const IdT *tx, const IdT *eq,
+                    const double *nobs, const EqT *equal, const double *rcw, const double *txl, bool d_mode,
                     qd::Result &R)
 {
     const size_t N = (size_t)n;
@@ -419,8 +424,24 @@ int run_device_pack(qdcuda::CudaExec &x, int64_t n, const int64_t *gene, const i
         up.cols[c] = qdcuda::Uploader::Col{d, src, N * sizeof(T)};
         return d;
     };
-    in.gene = col(qd::kColGene, gene, true); in.tx = col(qd::kColTx, tx, true); in.eq = col(qd::kColEq, eq, true);
-    in.nobs = col(qd::kColNobs, nobs, true); in.equal = col(qd::kColEqual, equal, true);
+    auto id_col = [&](int c, const IdT *src) -> const int64_t * {
+        const IdT *raw = col(c, src, true);
+        if (std::is_same<IdT, int64_t>::value || !raw) return reinterpret_cast<const int64_t *>(raw);
+        int64_t *wide = x.alloc<int64_t>(N);
+        x.on_arrival[c] = [&x, raw, wide, N] { x.pfor(N, [=] __device__(size_t i) { wide[i] = (int64_t)raw[i]; }); };
+        return wide;
+    };
+    in.gene = id_col(qd::kColGene, gene); in.tx = id_col(qd::kColTx, tx); in.eq = id_col(qd::kColEq, eq);
+    in.nobs = col(qd::kColNobs, nobs, true);
+    {
+        const EqT *raw = col(qd::kColEqual, equal, true);
+        if (std::is_same<EqT, uint8_t>::value || !raw) in.equal = reinterpret_cast<const uint8_t *>(raw);
+        else {
+            uint8_t *flag = x.alloc<uint8_t>(N);
+            x.on_arrival[qd::kColEqual] = [&x, raw, flag, N] { x.pfor(N, [=] __device__(size_t i) { flag[i] = raw[i] == 1 ? 1 : 0; }); };
+            in.equal = flag;                              // NA_LOGICAL (INT_MIN) counts as FALSE
+        }
+    }
     in.txl = col(qd::kColTxlen, txl, d_mode); in.rcw = col(qd::kColRcWidth, rcw, d_mode);
     up.start();
     x.up = &up;
@@ -434,6 +455,7 @@ int run_device_pack(qdcuda::CudaExec &x, int64_t n, const int64_t *gene, const i
     const int rc = qd::pack(x, in, R, err);
     const auto t_pack = std::chrono::steady_clock::now();
     up.finish();
+    for (auto &f : x.on_arrival) f = nullptr;
     if (getenv("BAMBU_PACK_TIMING")) {
         fprintf(stderr, "[device pack] pipeline done at %.2f ms; column copies staged at", std::chrono::duration<double, std::milli>(t_pack - up.t0).count());
         for (int c = 0; c < qd::kNumCols; ++c) fprintf(stderr, " %.2f", up.done_ms[c]);
@@ -452,7 +474,8 @@ void fetch(qdcuda::CudaExec &x, std::vector<T> &dst, const T *src, size_t n)
     x.d2h(dst.data(), src, n);
 }
 
-int check_args(bambu_quant_pack **out, int64_t n, const int64_t *gene_code, const int64_t *txid_in, const int64_t *eq_in,
+template <class IdT>
+int check_args(bambu_quant_pack **out, int64_t n, const IdT *gene_code, const IdT *txid_in, const IdT *eq_in,
                const double *nobs)
 {
     if (!out) { bambu_quant_set_error("NULL output"); return BAMBU_EM_EINVAL; }
@@ -466,6 +489,105 @@ int check_args(bambu_quant_pack **out, int64_t n, const int64_t *gene_code, cons
 }
 
 }  // namespace
+
+// the host-packer path for either input flavour (widens R's int columns first)
+inline int hostpack_any(int64_t n, const int64_t *g, const int64_t *t, const int64_t *e, const double *nobs, const uint8_t *equal,
+                        const double *rcw, const double *txl, int32_t bias, int32_t maxiter, double minvalue, double conv,
+                        int64_t *txid_out, double *counts, double *full_length, double *unique_counts, int64_t *n_result,
+                        double *d_rate)
+{
+    return bambu_quantDT_hostpack(n, g, t, e, nobs, equal, rcw, txl, bias, maxiter, minvalue, conv, txid_out, counts, full_length,
+                                  unique_counts, n_result, d_rate);
+}
+inline int hostpack_any(int64_t n, const int *g, const int *t, const int *e, const double *nobs, const int *equal,
+                        const double *rcw, const double *txl, int32_t bias, int32_t maxiter, double minvalue, double conv,
+                        int64_t *txid_out, double *counts, double *full_length, double *unique_counts, int64_t *n_result,
+                        double *d_rate)
+{
+    const size_t N = (size_t)n;
+    std::vector<int64_t> g64(N), t64(N), e64(N);
+    std::vector<uint8_t> eqf(N);
+    for (size_t i = 0; i < N; ++i) { g64[i] = g[i]; t64[i] = t[i]; e64[i] = e[i]; }
+    if (equal) for (size_t i = 0; i < N; ++i) eqf[i] = equal[i] == 1;
+    return bambu_quantDT_hostpack(n, g64.data(), t64.data(), e64.data(), nobs, equal ? eqf.data() : nullptr, rcw, txl, bias, maxiter,
+                                  minvalue, conv, txid_out, counts, full_length, unique_counts, n_result, d_rate);
+}
+
+template <class IdT, class EqT>
+int quantdt_core(int64_t n, const IdT *gene_code, const IdT *txid, const IdT *eqClassId, const double *nobs,
+                  const EqT *equal, const double *rcWidth, const double *txlen, int32_t degradation_bias,
+                  int32_t maxiter, double minvalue, double conv, int64_t *txid_out, double *counts, double *full_length,
+                  double *unique_counts, int64_t *n_result, double *d_rate_out)
+{
+    const char *force_host = getenv("BAMBU_QUANT_HOST_PACK");
+    if (force_host && force_host[0] == '1')
+        return hostpack_any(n, gene_code, txid, eqClassId, nobs, equal, rcWidth, txlen, degradation_bias, maxiter,
+                            minvalue, conv, txid_out, counts, full_length, unique_counts, n_result, d_rate_out);
+    bambu_quant_pack *dummy = nullptr;
+    int rc = check_args(&dummy, n, gene_code, txid, eqClassId, nobs);
+    if (rc) return rc;
+    if (!txid_out || !counts || !full_length || !unique_counts || !n_result) { bambu_quant_set_error("NULL output"); return BAMBU_EM_EINVAL; }
+    rc = bambu_em_internal_ensure_device();
+    if (rc) { bambu_quant_set_error(bambu_em_last_error()); return rc; }
+    if (!qdcuda::g_ws.ensure(qdcuda::workspace_bytes((size_t)n))) {
+        bambu_quant_set_error("not enough device memory for the packer workspace");
+        return BAMBU_EM_ENOMEM;
+    }
+    const bool timing = getenv("BAMBU_PACK_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    const auto t0 = now();
+    bambu_quant_pack P;
+    try {
+        qdcuda::CudaExec x(qdcuda::g_ws.st, qdcuda::g_ws.pool, qdcuda::g_ws.cap, qdcuda::g_ws.sms);
+        qd::Result R;
+        rc = run_device_pack(x, n, gene_code, txid, eqClassId, nobs, equal, rcWidth, txlen, degradation_bias != 0, R);
+        if (rc == 1)
+            return hostpack_any(n, gene_code, txid, eqClassId, nobs, equal, rcWidth, txlen, degradation_bias, maxiter,
+                                minvalue, conv, txid_out, counts, full_length, unique_counts, n_result, d_rate_out);
+        if (rc) return rc;
+        fetch(x, P.grp_row_ptr, R.grp_row_ptr, (size_t)R.n_groups + 1);
+        fetch(x, P.grp_col_ptr, R.grp_col_ptr, (size_t)R.n_groups + 1);
+        fetch(x, P.row_nnz_ptr, R.row_nnz_ptr, (size_t)R.n_rows + 1);
+        fetch(x, P.txid, R.txid, (size_t)R.n_rows);
+        P.out_txid.swap(R.out_txid);
+        P.unobserved_txid.swap(R.unobserved_txid);
+        P.d_rate = R.d_rate;
+        QD_CUDA(cudaGetLastError());
+        const auto t1 = now();
+        std::vector<double> est((size_t)std::max<int64_t>(3 * (int64_t)R.n_rows, 1));
+        if (R.n_groups) {
+            // one cached plan: its device buffers only grow, so repeated calls allocate nothing
+            bambu_em_plan *&plan = qdcuda::g_plan;
+            rc = plan ? bambu_em_plan_reset(plan, R.n_groups, P.grp_row_ptr.data(), P.grp_col_ptr.data(), P.row_nnz_ptr.data())
+                      : bambu_em_plan_create(&plan, R.n_groups, P.grp_row_ptr.data(), P.grp_col_ptr.data(), P.row_nnz_ptr.data());
+            if (!rc) rc = bambu_em_plan_bind_device(plan, R.col_idx, R.aval, R.nz_flags, R.Y, R.K, R.col_flags);
+            if (!rc) rc = bambu_em_plan_run(plan, maxiter, minvalue, conv);
+            if (!rc) rc = bambu_em_plan_download(plan, est.data(), nullptr, nullptr, nullptr);
+            if (rc) {
+                bambu_quant_set_error(bambu_em_last_error());
+                if (plan) bambu_em_plan_destroy(plan);
+                plan = nullptr;
+                return rc;
+            }
+        }
+        const auto t2 = now();
+        rc = bambu_quant_merge(&P, est.data(), txid_out, counts, full_length, unique_counts, n_result);
+        if (!rc && d_rate_out) *d_rate_out = P.d_rate;
+        if (timing)
+            fprintf(stderr, "[bambu_quantDT] rows %lld: H2D + device pack %.2f ms (%ld launches), EM %.2f ms, merge %.2f ms\n",
+                    (long long)n, ms(t0, t1), x.launches, ms(t1, t2), ms(t2, now()));
+        return rc;
+    } catch (const qdcuda::CudaError &e) {
+        bambu_quant_set_error(std::string("CUDA error in the device packer: ") + cudaGetErrorString(e.e) + " (" + e.what + ")");
+        return BAMBU_EM_ECUDA;
+    } catch (const std::bad_alloc &) {
+        bambu_quant_set_error("out of memory in the device packer");
+        return BAMBU_EM_ENOMEM;
+    }
+}
 
 extern "C" {
 
@@ -534,74 +656,8 @@ int bambu_quantDT(int64_t n, const int64_t *gene_code, const int64_t *txid, cons
                   int32_t maxiter, double minvalue, double conv, int64_t *txid_out, double *counts, double *full_length,
                   double *unique_counts, int64_t *n_result, double *d_rate_out)
 {
-    const char *force_host = getenv("BAMBU_QUANT_HOST_PACK");
-    if (force_host && force_host[0] == '1')
-        return bambu_quantDT_hostpack(n, gene_code, txid, eqClassId, nobs, equal, rcWidth, txlen, degradation_bias, maxiter,
-                                      minvalue, conv, txid_out, counts, full_length, unique_counts, n_result, d_rate_out);
-    bambu_quant_pack *dummy = nullptr;
-    int rc = check_args(&dummy, n, gene_code, txid, eqClassId, nobs);
-    if (rc) return rc;
-    if (!txid_out || !counts || !full_length || !unique_counts || !n_result) { bambu_quant_set_error("NULL output"); return BAMBU_EM_EINVAL; }
-    rc = bambu_em_internal_ensure_device();
-    if (rc) { bambu_quant_set_error(bambu_em_last_error()); return rc; }
-    if (!qdcuda::g_ws.ensure(qdcuda::workspace_bytes((size_t)n))) {
-        bambu_quant_set_error("not enough device memory for the packer workspace");
-        return BAMBU_EM_ENOMEM;
-    }
-    const bool timing = getenv("BAMBU_PACK_TIMING") != nullptr;
-    auto now = [] { return std::chrono::steady_clock::now(); };
-    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
-        return std::chrono::duration<double, std::milli>(b - a).count();
-    };
-    const auto t0 = now();
-    bambu_quant_pack P;
-    try {
-        qdcuda::CudaExec x(qdcuda::g_ws.st, qdcuda::g_ws.pool, qdcuda::g_ws.cap, qdcuda::g_ws.sms);
-        qd::Result R;
-        rc = run_device_pack(x, n, gene_code, txid, eqClassId, nobs, equal, rcWidth, txlen, degradation_bias != 0, R);
-        if (rc == 1)
-            return bambu_quantDT_hostpack(n, gene_code, txid, eqClassId, nobs, equal, rcWidth, txlen, degradation_bias, maxiter,
-                                          minvalue, conv, txid_out, counts, full_length, unique_counts, n_result, d_rate_out);
-        if (rc) return rc;
-        fetch(x, P.grp_row_ptr, R.grp_row_ptr, (size_t)R.n_groups + 1);
-        fetch(x, P.grp_col_ptr, R.grp_col_ptr, (size_t)R.n_groups + 1);
-        fetch(x, P.row_nnz_ptr, R.row_nnz_ptr, (size_t)R.n_rows + 1);
-        fetch(x, P.txid, R.txid, (size_t)R.n_rows);
-        P.out_txid.swap(R.out_txid);
-        P.unobserved_txid.swap(R.unobserved_txid);
-        P.d_rate = R.d_rate;
-        QD_CUDA(cudaGetLastError());
-        const auto t1 = now();
-        std::vector<double> est((size_t)std::max<int64_t>(3 * (int64_t)R.n_rows, 1));
-        if (R.n_groups) {
-            // one cached plan: its device buffers only grow, so repeated calls allocate nothing
-            bambu_em_plan *&plan = qdcuda::g_plan;
-            rc = plan ? bambu_em_plan_reset(plan, R.n_groups, P.grp_row_ptr.data(), P.grp_col_ptr.data(), P.row_nnz_ptr.data())
-                      : bambu_em_plan_create(&plan, R.n_groups, P.grp_row_ptr.data(), P.grp_col_ptr.data(), P.row_nnz_ptr.data());
-            if (!rc) rc = bambu_em_plan_bind_device(plan, R.col_idx, R.aval, R.nz_flags, R.Y, R.K, R.col_flags);
-            if (!rc) rc = bambu_em_plan_run(plan, maxiter, minvalue, conv);
-            if (!rc) rc = bambu_em_plan_download(plan, est.data(), nullptr, nullptr, nullptr);
-            if (rc) {
-                bambu_quant_set_error(bambu_em_last_error());
-                if (plan) bambu_em_plan_destroy(plan);
-                plan = nullptr;
-                return rc;
-            }
-        }
-        const auto t2 = now();
-        rc = bambu_quant_merge(&P, est.data(), txid_out, counts, full_length, unique_counts, n_result);
-        if (!rc && d_rate_out) *d_rate_out = P.d_rate;
-        if (timing)
-            fprintf(stderr, "[bambu_quantDT] rows %lld: H2D + device pack %.2f ms (%ld launches), EM %.2f ms, merge %.2f ms\n",
-                    (long long)n, ms(t0, t1), x.launches, ms(t1, t2), ms(t2, now()));
-        return rc;
-    } catch (const qdcuda::CudaError &e) {
-        bambu_quant_set_error(std::string("CUDA error in the device packer: ") + cudaGetErrorString(e.e) + " (" + e.what + ")");
-        return BAMBU_EM_ECUDA;
-    } catch (const std::bad_alloc &) {
-        bambu_quant_set_error("out of memory in the device packer");
-        return BAMBU_EM_ENOMEM;
-    }
+    return quantdt_core(n, gene_code, txid, eqClassId, nobs, equal, rcWidth, txlen, degradation_bias, maxiter, minvalue, conv,
+                        txid_out, counts, full_length, unique_counts, n_result, d_rate_out);
 }
 
 // bambu_quantDT for R's .C() interface, which needs no compiled shim: every argument is a pointer to one of R's
@@ -620,15 +676,10 @@ void bambu_quantDT_dotC(const int *n_rows, const int *gene_code, const int *txid
     }
     const size_t N = (size_t)*n_rows;
     try {
-        std::vector<int64_t> g(N), t(N), e(N), t_out(std::max<size_t>(N, 1));
-        std::vector<uint8_t> eqf(N);
-        if (N && (!gene_code || !txid || !eqClassId)) { bambu_quant_set_error("Columns GENEID, txid, eqClassId, nobs, are missing from object."); *rc = BAMBU_EM_EINVAL; return; }
-        for (size_t i = 0; i < N; ++i) { g[i] = gene_code[i]; t[i] = txid[i]; e[i] = eqClassId[i]; }
-        if (equal) for (size_t i = 0; i < N; ++i) eqf[i] = equal[i] == 1;       // NA_LOGICAL (INT_MIN) counts as FALSE
+        std::vector<int64_t> t_out(std::max<size_t>(N, 1));
         int64_t k = 0;
-        *rc = bambu_quantDT((int64_t)N, g.data(), t.data(), e.data(), nobs, equal ? eqf.data() : nullptr, rcWidth, txlen,
-                            *degradation_bias, *maxiter, *minvalue, *conv, t_out.data(), counts, full_length, unique_counts,
-                            &k, d_rate);
+        *rc = quantdt_core((int64_t)N, gene_code, txid, eqClassId, nobs, equal, rcWidth, txlen, *degradation_bias, *maxiter,
+                           *minvalue, *conv, t_out.data(), counts, full_length, unique_counts, &k, d_rate);
         if (*rc == BAMBU_EM_OK) {
             if (txid_out) for (int64_t q = 0; q < k; ++q) txid_out[q] = (int)t_out[(size_t)q];
             *n_result = (int)k;
