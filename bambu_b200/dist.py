@@ -75,9 +75,14 @@ class EstimateGatherer:
     """Reusable gather of per-rank ``est[3, rows_r]`` tables to ``dst``: device staging
     buffers and the pinned host result are allocated once (cohort steps repeat the same
     shapes).  ``__call__`` takes this rank's pinned host table and returns, on ``dst``, a
-    list of pinned host tensors (views, overwritten by the next call)."""
+    list of pinned host tensors (views, overwritten by the next call).
 
-    def __init__(self, rows_local: int, device, dst: int = 0, group=None):
+    ``overlap=True``: the upload of the table, the collective and ``dst``'s download are queued on a side
+    stream and ``__call__`` returns at once, so the next step's EM runs while the previous step's tables
+    travel; ``wait()`` (also called at the start of the next ``__call__``) completes them.  The caller must
+    not overwrite the host table it passed before the next ``wait()`` -- alternate two tables."""
+
+    def __init__(self, rows_local: int, device, dst: int = 0, group=None, overlap: bool = False):
         import torch
         import torch.distributed as dist
         self.dist, self.torch, self.group, self.dst = dist, torch, group, dst
@@ -94,15 +99,34 @@ class EstimateGatherer:
             self.recv = [torch.empty_like(self.send) for _ in range(self.world)]
             pin = self.device.type == "cuda"
             self.host = [torch.empty((3, n), dtype=torch.float64, pin_memory=pin) for n in self.rows]
+        self.overlap = bool(overlap) and self.device.type == "cuda"
+        self.stream = torch.cuda.Stream(self.device) if self.overlap else None
+        self.pending = False
+
+    def _enqueue(self, t):
+        self.send[:, :t.shape[1]].copy_(t, non_blocking=True)
+        self.dist.gather(self.send, self.recv, dst=self.dst, group=self.group)
+        if self.rank == self.dst:
+            for h, d, n in zip(self.host, self.recv, self.rows):
+                h.copy_(d[:, :n], non_blocking=True)
+
+    def wait(self):
+        if self.pending:
+            self.stream.synchronize()
+            self.pending = False
+        return self.host
 
     def __call__(self, est_host):
         t = est_host if isinstance(est_host, self.torch.Tensor) else self.torch.from_numpy(est_host)
-        self.send[:, :t.shape[1]].copy_(t, non_blocking=True)
-        self.dist.gather(self.send, self.recv, dst=self.dst, group=self.group)
+        if self.overlap:
+            self.wait()
+            with self.torch.cuda.stream(self.stream):
+                self._enqueue(t)
+            self.pending = True
+            return None
+        self._enqueue(t)
         if self.rank != self.dst:
             return None
-        for h, d, n in zip(self.host, self.recv, self.rows):
-            h.copy_(d[:, :n], non_blocking=True)
         if self.device.type == "cuda":
             self.torch.cuda.current_stream(self.device).synchronize()
         return self.host
