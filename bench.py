@@ -193,6 +193,23 @@ def quantdt_stage(args):
                     "counts by txid), median of 5; ms_host_packer = the same with csrc/quant_pack.cpp in front"}
 
 
+def bind_to_gpu_numa_node(local):
+    """Keep this rank's host threads -- and with them the first-touched pinned buffers -- on the CPUs next to its GPU
+    (NVML's ideal affinity), so that eight ranks do not pull their arenas across the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:          # no NVML / not permitted: run unbound
+        return 0
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -204,6 +221,7 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    bound_cpus = bind_to_gpu_numa_node(local) if world > 1 else 0
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     _lib.check(_lib.lib().bambu_em_set_device(local))
@@ -347,7 +365,7 @@ def run_b200(args):
                                       "(columns with Y != 0, aval != 0)"},
             "work": {"nnz_iterations_per_step": work_all, "live_nnz_iterations_per_step": live_all,
                      "groups_per_gpu": n_groups, "max_iters": int(iters.max()), "median_iters": float(np.median(iters)),
-                     "last_step_ms": last, "gen_seconds": gen_s},
+                     "last_step_ms": last, "gen_seconds": gen_s, "cpus_bound_to_gpu_numa_node": bound_cpus},
         }
         if world == 1 and not args.no_cpu:
             import oracle
