@@ -291,6 +291,25 @@ def run_b200(args):
     work_all, live_all = float(tot[1]), float(tot[2])
     value = work_all * args.steps / (ms * 1e-3)
 
+    # ---- the stages on their own: H2D of the arena / pack + EM kernels / D2H of the outputs, each between
+    #      CUDA events on the plan's stream, median of 5 -------------------------------------------------------------
+    def staged():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record(stream)
+        plan.upload_ptrs(*[pinned[n].data_ptr() for n in payload])
+        ev[1].record(stream)
+        plan.run(**EM_PAR)
+        plan.sync()
+        r = plan.last_run_ms()
+        ev[2].record(stream)
+        plan.download_ptrs(h_est.data_ptr(), h_iters.data_ptr(), h_status.data_ptr())
+        ev[3].record(stream)
+        torch.cuda.synchronize()
+        return ev[0].elapsed_time(ev[1]), r["pack_ms"], r["em_ms"], ev[2].elapsed_time(ev[3])
+    st = np.median(np.array([staged() for _ in range(5)]), axis=0)
+    stages = {"h2d_ms": float(st[0]), "pack_ms": float(st[1]), "em_ms": float(st[2]), "d2h_ms": float(st[3]),
+              "sum_ms": float(st.sum()), "note": "one GPU's slab, stages serialised (the pipelined e2e overlaps them)"}
+
     # ---- end to end through the C-ABI with host buffers ------------------------------------
     gatherer = None
     if world > 1:     # outputs to rank 0 (the reference's combineCountSes cbind, R/bambu_utilityFunctions.R:215-241)
@@ -347,6 +366,7 @@ def run_b200(args):
                     "ms_per_step": e2e_s / args.steps * 1e3,
                     "timer": "host wall clock around bambu_em_batched (plan + H2D + kernels + D2H"
                              + (" + NCCL gather to rank 0 and its D2H, overlapped with the next step's EM)" if world > 1 else ")")},
+            "stages_ms": stages,
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
