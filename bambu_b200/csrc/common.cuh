@@ -89,14 +89,19 @@ __host__ __device__ inline uint32_t pack_smem_bytes(uint32_t M, uint32_t N)
 // lane-minor, so that a warp reads 32 consecutive values (no bank conflicts) and runs
 // a loop whose trip count is uniform (no divergence, no parity branch).
 //
-//   [rs f64 M][Yl f64 NL]
+// Lines live in POSITION order (position p = 32*slice + lane, lines sorted by length): the EM kernel's
+// vectors theta / ratio and the per-line constants below are all indexed by position, so a lane finds its
+// own line's data at a fixed place and only the gathers go through stored offsets.
+//
+//   [rs f64 M][Yl f64 NL]                                             (by position)
 //   [row side : slotsR x {(valE, valO) f64x2 x32 | offE u16 x32 | offO u16 x32}]        640 B / slot
 //               (an index is stored as the byte offset of the gathered element in the EM
-//                kernel's vector region -- theta[M+1] then ratio[NL+1] -- so 8*(M+NL+2) < 65536)
+//                kernel's vector region -- theta[M+1] then ratio[NL+1], by position -- so 8*(M+NL+2) < 65536)
 //   [col side : slotsC x {same}]
-//   [rowid u16 32*nSliceR][colid u16 32*nSliceC][startR u32 nSliceR+1][startC u32 nSliceC+1]
+//   [descR u32x2 nSliceR][descC u32x2 nSliceC]   {byte offset of the slice's first slot in its side, slots}
 //                                                                   <- copied to shared memory
-//   [KY f64 NL][cm u8 NL+1][eq u8 : slotsR x {E x32 | O x32}]        <- read once, in the epilogue
+//   [KY f64 NL][cm u8 NL+1] (by position) [rowid u16 M: row at each position][eq u8 : slotsR x {E x32 | O x32}]
+//                                                                   <- read once, in the epilogue
 struct GroupImg {
     uint32_t off16;       // image offset inside the pool, in 16-byte units
     uint32_t smem_bytes;  // shared memory the EM kernel needs; 0 = not queued
@@ -111,7 +116,7 @@ static_assert(sizeof(GroupImg) == 32, "GroupImg layout");
 constexpr uint32_t kSlotBytes = 640;
 
 struct SellLayout {
-    uint32_t rs, Yl, sideR, sideC, rowid, colid, startR, startC, copy_bytes, KY, cm, eq, total;
+    uint32_t rs, Yl, sideR, sideC, descR, descC, copy_bytes, KY, cm, rowid, eq, total;
 };
 
 __host__ __device__ inline SellLayout sell_layout(uint32_t M, uint32_t NL, uint32_t nSliceR, uint32_t nSliceC,
@@ -122,14 +127,13 @@ __host__ __device__ inline SellLayout sell_layout(uint32_t M, uint32_t NL, uint3
     L.Yl = 8u * M;
     L.sideR = align_up(L.Yl + 8u * NL, 16);   // slots are read as double2
     L.sideC = L.sideR + kSlotBytes * slotsR;
-    L.rowid = L.sideC + kSlotBytes * slotsC;
-    L.colid = L.rowid + 64u * nSliceR;
-    L.startR = L.colid + 64u * nSliceC;
-    L.startC = L.startR + 4u * (nSliceR + 1);
-    L.copy_bytes = align_up(L.startC + 4u * (nSliceC + 1), 16);
+    L.descR = L.sideC + kSlotBytes * slotsC;
+    L.descC = L.descR + 8u * nSliceR;
+    L.copy_bytes = align_up(L.descC + 8u * nSliceC, 16);
     L.KY = L.copy_bytes;
     L.cm = L.KY + 8u * NL;
-    L.eq = align_up(L.cm + NL + 1, 16);
+    L.rowid = align_up(L.cm + NL + 1, 2);
+    L.eq = align_up(L.rowid + 2u * M, 16);
     L.total = align_up(L.eq + 64u * slotsR, 16);
     return L;
 }

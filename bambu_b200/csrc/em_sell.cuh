@@ -10,10 +10,11 @@
 // one live column in the E-phase and one row in the M-phase; a warp owns slices of 32;
 // a CTA owns one group at a time and pulls groups from its class's queue.
 //
-// Shared memory: [theta f64 M+1][ratio f64 NL+1][image].  The image stores every index as
-// the byte offset of the gathered element in that vector region, so a gather needs no
-// address arithmetic.  theta[M] and ratio[NL] are always 0.0: padding entries (value 0.0)
-// point there and add an exact +0.0.
+// Shared memory: [theta f64 M+1][ratio f64 NL+1][image].  Both vectors and the per-line constants
+// (rs, Y) are stored BY POSITION (32*slice + lane), so a lane's own line needs no index lookup, and
+// the image stores every gathered index as the byte offset of the element in that vector region, so
+// a gather needs no address arithmetic.  theta[M] and ratio[NL] are always 0.0: padding entries
+// (value 0.0) point there and add an exact +0.0.
 //
 // FP64 throughout; products and sums use the non-contracting intrinsics: the reference
 // rounds a_ij*theta_i before it is summed (src/em.cpp:46-47), so no FMA may be formed.
@@ -70,12 +71,12 @@ __device__ __forceinline__ double vec_at(const uint8_t *vec, uint32_t off)
 }
 
 template <int MODE>
-__device__ __forceinline__ void line_sums(const uint8_t *__restrict__ side, uint32_t s0, uint32_t s1, int lane,
+__device__ __forceinline__ void line_sums(const uint8_t *__restrict__ side, uint2 desc, int lane,
                                           const uint8_t *__restrict__ vec, double &a1, double &a2, int &cnt)
 {
-    const uint8_t *p = side + (size_t)kSlotBytes * s0;
+    const uint8_t *p = side + desc.x;        // desc = {byte offset of the slice's first slot, slots}
 #pragma unroll kSlotUnroll
-    for (uint32_t s = s0; s < s1; ++s, p += kSlotBytes) {
+    for (uint32_t s = 0; s < desc.y; ++s, p += kSlotBytes) {
         const double2 v = reinterpret_cast<const double2 *>(p)[lane];
         const uint32_t oe = reinterpret_cast<const uint16_t *>(p + 512)[lane];
         const uint32_t oo = reinterpret_cast<const uint16_t *>(p + 576)[lane];
@@ -151,10 +152,8 @@ em_sell_kernel(const int32_t *__restrict__ queue, const int *__restrict__ qcount
         const double *Yl = reinterpret_cast<const double *>(simg + L.Yl);
         const uint8_t *sideR = simg + L.sideR;
         const uint8_t *sideC = simg + L.sideC;
-        const uint16_t *rowid = reinterpret_cast<const uint16_t *>(simg + L.rowid);
-        const uint16_t *colid = reinterpret_cast<const uint16_t *>(simg + L.colid);
-        const uint32_t *startR = reinterpret_cast<const uint32_t *>(simg + L.startR);
-        const uint32_t *startC = reinterpret_cast<const uint32_t *>(simg + L.startC);
+        const uint2 *descR = reinterpret_cast<const uint2 *>(simg + L.descR);
+        const uint2 *descC = reinterpret_cast<const uint2 *>(simg + L.descC);
         double *theta = reinterpret_cast<double *>(smem);                   // M + 1, theta[M] = 0 (padding target)
         double *ratio = theta + (M + 1);                                    // NL + 1, ratio[NL] = 0
         for (int i = tid; i < M; i += T) theta[i] = 1.0;                    // src/em.cpp:20-21
@@ -179,15 +178,15 @@ em_sell_kernel(const int32_t *__restrict__ queue, const int *__restrict__ qcount
             if (tid == 0) s_nf[par] = 0;
             // E-phase: c_j = sum_i a_ij*theta_i (:46-47), ratio_j = Y_j / c_j (:48)
             for (int sl = warp; sl < nSliceC; sl += NW) {
-                const int j = colid[sl * 32 + lane];
+                const int j = sl * 32 + lane;          // the lane's column, by position
                 double a1 = 0.0, a2 = 0.0;
                 int cnt = 0;
                 if (nP == 0) {
-                    line_sums<0>(sideC, startC[sl], startC[sl + 1], lane, vec, a1, a2, cnt);
+                    line_sums<0>(sideC, descC[sl], lane, vec, a1, a2, cnt);
                 } else {
                     // dense semantics: a row with non-finite theta poisons every column it has a
                     // structural zero in (0*NaN), SURVEY Appendix C.14
-                    line_sums<1>(sideC, startC[sl], startC[sl + 1], lane, vec, a1, a2, cnt);
+                    line_sums<1>(sideC, descC[sl], lane, vec, a1, a2, cnt);
                     if (cnt < nP) a1 = qnan();
                 }
                 if (j < NL) {
@@ -202,11 +201,12 @@ em_sell_kernel(const int32_t *__restrict__ queue, const int *__restrict__ qcount
             if (tid == 0) s_rbad[par ^ 1] = 0;
             int flag = (P.conv < 0.0) ? 1 : 0;   // delta >= 0 > conv whenever conv is negative
             for (int sl = warp; sl < nSliceR; sl += NW) {
-                const int i = rowid[sl * 32 + lane];
-                const double th = theta[i];      // i == M on padding lanes: 0.0
+                const int i = sl * 32 + lane;        // the lane's row, by position
+                const double th = theta[min(i, M)];  // padding lanes read theta[M] = 0.0
                 double a1 = 0.0, a2 = 0.0;
-                const uint8_t *p = sideR + (size_t)kSlotBytes * startR[sl];
-                const uint32_t ns = startR[sl + 1] - startR[sl];
+                const uint2 d = descR[sl];
+                const uint8_t *p = sideR + d.x;
+                const uint32_t ns = d.y;
                 if (!hazard) {
 #pragma unroll kSlotUnroll
                     for (uint32_t s = 0; s < ns; ++s, p += kSlotBytes) {
@@ -258,11 +258,12 @@ em_sell_kernel(const int32_t *__restrict__ queue, const int *__restrict__ qcount
         const uint8_t *cm = gimg + L.cm;
         const uint8_t *eq = gimg + L.eq;
         const uint32_t ratio_off = 8u * (uint32_t)(M + 1);
+        const uint16_t *rowid = reinterpret_cast<const uint16_t *>(gimg + L.rowid);
         for (int sl = warp; sl < nSliceC; sl += NW) {
-            const int j = colid[sl * 32 + lane];
+            const int j = sl * 32 + lane;
             double a1 = 0.0, a2 = 0.0;
             int cnt = 0;
-            line_sums<1>(sideC, startC[sl], startC[sl + 1], lane, vec, a1, a2, cnt);
+            line_sums<1>(sideC, descC[sl], lane, vec, a1, a2, cnt);
             if (j < NL) {
                 double c = __dadd_rn(a1, a2);
                 if (cnt < nP) c = qnan();
@@ -276,18 +277,19 @@ em_sell_kernel(const int32_t *__restrict__ queue, const int *__restrict__ qcount
         const int Q = s_Q;
         int bad = 0;
         for (int sl = warp; sl < nSliceR; sl += NW) {
-            const int i = rowid[sl * 32 + lane];
-            const double th = theta[i];
+            const int pos = sl * 32 + lane;
+            const double th = theta[min(pos, M)];
             double t1 = 0, t2 = 0, f1 = 0, f2 = 0, u1 = 0, u2 = 0;
             int cnt = 0;
-            const uint32_t s0 = startR[sl], s1 = startR[sl + 1];
-            const uint8_t *p = sideR + (size_t)kSlotBytes * s0;
+            const uint2 d = descR[sl];
+            const uint32_t s0 = d.x / kSlotBytes, s1 = s0 + d.y;
+            const uint8_t *p = sideR + d.x;
             for (uint32_t s = s0; s < s1; ++s, p += kSlotBytes) {
                 const double2 v2 = reinterpret_cast<const double2 *>(p)[lane];
                 const double ve = v2.x, vo = v2.y;
                 const uint32_t oe = reinterpret_cast<const uint16_t *>(p + 512)[lane];
                 const uint32_t oo = reinterpret_cast<const uint16_t *>(p + 576)[lane];
-                const uint32_t ie = (oe - ratio_off) >> 3, io = (oo - ratio_off) >> 3;   // live column index
+                const uint32_t ie = (oe - ratio_off) >> 3, io = (oo - ratio_off) >> 3;   // column position (cm is by position)
                 const double be = vec_at(vec, oe), bo = vec_at(vec, oo);
                 const double fe = __ldg(eq + (size_t)64 * s + lane) ? ve : __dmul_rn(ve, 0.0);        // fullAval = aval*equal
                 const double fo = __ldg(eq + (size_t)64 * s + 32 + lane) ? vo : __dmul_rn(vo, 0.0);
@@ -301,7 +303,8 @@ em_sell_kernel(const int32_t *__restrict__ queue, const int *__restrict__ qcount
                 u1 = __dadd_rn(u1, __dmul_rn(__dmul_rn(ue, th), be));
                 u2 = __dadd_rn(u2, __dmul_rn(__dmul_rn(uo, th), bo));
             }
-            if (i < M) {
+            if (pos < M) {
+                const int i = __ldg(rowid + pos);       // the row this position holds
                 double e0 = __dadd_rn(t1, t2), e1 = __dadd_rn(f1, f2), e2 = __dadd_rn(u1, u2);
                 // dense 0*NaN / 0*Inf at the structural zeros of this row
                 if (!is_finite(th) || cnt < Q) e0 = e1 = e2 = qnan();

@@ -11,7 +11,7 @@
 namespace bambu {
 
 struct SellSide {
-    uint16_t *L;      // n          slots needed per line
+    uint16_t *L;      // n          slots needed per line; after sell_measure: the line's position
     uint16_t *id;     // 32*nSlice  line at each position (n = padding)
     uint32_t *start;  // nSlice+1   first slot of each slice
     int n, nSlice;
@@ -56,18 +56,20 @@ __device__ __forceinline__ void sell_measure(SellSide &S, const uint16_t *__rest
     __syncthreads();
     S.slots = block_excl_scan<T>(S.start, S.nSlice, s_warp);
     if (tid == 0) S.start[S.nSlice] = S.slots;
+    for (int p = tid; p < n; p += T) S.L[S.id[p]] = (uint16_t)p;     // lengths are done with: line -> position
     __syncthreads();
 }
 
 // write one side's slots.  Slot = { (valE, valO) x 32 lanes | offE u16 x 32 | offO u16 x 32 };
 // an index is stored as the BYTE OFFSET of the gathered element inside the EM kernel's vector
 // region (theta at 0, ratio behind it): off = vec_off + 8 * index.  dummy = offset of the
-// always-zero element of the vector this side gathers from.  eq_out/eq_in: per-entry "equal"
-// flags (row side only).
+// always-zero element of the vector this side gathers from.  pos_other: position of every line of the
+// OTHER side (the gathered vector is stored by position).  eq_out/eq_in: per-entry "equal" flags (row side only).
 template <int T>
 __device__ __forceinline__ void sell_fill(const SellSide &S, const uint16_t *__restrict__ ptr,
                                           const uint16_t *__restrict__ idx, const double *__restrict__ val,
                                           uint8_t *__restrict__ side, uint32_t vec_off, uint16_t dummy,
+                                          const uint16_t *__restrict__ pos_other,
                                           const uint8_t *__restrict__ eq_in, uint8_t *__restrict__ eq_out)
 {
     const int tid = threadIdx.x;
@@ -80,7 +82,7 @@ __device__ __forceinline__ void sell_fill(const SellSide &S, const uint16_t *__r
             for (int k = ptr[i]; k < ptr[i + 1]; ++k) {
                 const uint16_t ix = idx[k];
                 const double v = val[k];
-                const uint16_t off = (uint16_t)(vec_off + 8u * (uint32_t)(ix >> 1));
+                const uint16_t off = (uint16_t)(vec_off + 8u * (uint32_t)pos_other[ix >> 1]);
                 if (ix & 1) {
                     uint8_t *slot = base + (size_t)kSlotBytes * ko;
                     reinterpret_cast<double *>(slot)[2 * lane + 1] = v;
@@ -183,24 +185,23 @@ sell_kernel(const int32_t *__restrict__ work, int n_work, const int64_t *__restr
         double *Yl = reinterpret_cast<double *>(img + L.Yl);
         double *KY = reinterpret_cast<double *>(img + L.KY);
         uint8_t *cm = img + L.cm;
-        for (int i = tid; i < M; i += T) rs[i] = rs1[i];
-        for (int j = tid; j < NL; j += T) { Yl[j] = Y1[j]; KY[j] = KY1[j]; cm[j] = cm1[j]; }
+        // per-line constants by POSITION (R.id / C.id: line at each position)
+        for (int p = tid; p < M; p += T) rs[p] = rs1[R.id[p]];
+        for (int p = tid; p < NL; p += T) { const int j = C.id[p]; Yl[p] = Y1[j]; KY[p] = KY1[j]; cm[p] = cm1[j]; }
         if (tid == 0) cm[NL] = 0;
         uint16_t *rowid = reinterpret_cast<uint16_t *>(img + L.rowid);
-        uint16_t *colid = reinterpret_cast<uint16_t *>(img + L.colid);
-        uint32_t *startR = reinterpret_cast<uint32_t *>(img + L.startR);
-        uint32_t *startC = reinterpret_cast<uint32_t *>(img + L.startC);
-        for (int p = tid; p < 32 * R.nSlice; p += T) rowid[p] = R.id[p];
-        for (int p = tid; p < 32 * C.nSlice; p += T) colid[p] = C.id[p];
-        for (int w = tid; w <= R.nSlice; w += T) startR[w] = R.start[w];
-        for (int w = tid; w <= C.nSlice; w += T) startC[w] = C.start[w];
+        uint2 *descR = reinterpret_cast<uint2 *>(img + L.descR);
+        uint2 *descC = reinterpret_cast<uint2 *>(img + L.descC);
+        for (int p = tid; p < M; p += T) rowid[p] = R.id[p];
+        for (int w = tid; w < R.nSlice; w += T) descR[w] = make_uint2(kSlotBytes * R.start[w], R.start[w + 1] - R.start[w]);
+        for (int w = tid; w < C.nSlice; w += T) descC[w] = make_uint2(kSlotBytes * C.start[w], C.start[w + 1] - C.start[w]);
     }
     // vector region of the EM kernel: theta[M+1] at byte 0, ratio[NL+1] behind it.  The row side
     // gathers ratio[] (dummy element NL), the column side gathers theta[] (dummy element M).
     const uint32_t ratio_off = 8u * (uint32_t)(M + 1);
-    sell_fill<T>(R, rp, cidx, cval, img + L.sideR, ratio_off, (uint16_t)(ratio_off + 8u * (uint32_t)NL), img1 + L1.eq,
+    sell_fill<T>(R, rp, cidx, cval, img + L.sideR, ratio_off, (uint16_t)(ratio_off + 8u * (uint32_t)NL), C.L, img1 + L1.eq,
                  img + L.eq);
-    sell_fill<T>(C, cp, ridx, rval, img + L.sideC, 0u, (uint16_t)(8u * (uint32_t)M), nullptr, nullptr);
+    sell_fill<T>(C, cp, ridx, rval, img + L.sideC, 0u, (uint16_t)(8u * (uint32_t)M), R.L, nullptr, nullptr);
 
     if (tid == 0) {
         GroupImg gi;
