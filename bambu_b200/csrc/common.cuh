@@ -233,6 +233,7 @@ __device__ __forceinline__ void sort_column(IdxT *idx, double *val, uint32_t lo,
     }
 }
 
-__device__ __forceinline__ bool is_finite(double x) { return fabs(x) <= 1.7976931348623157e308; }
+// exponent field not all ones; an integer test on the high word keeps it off the FP64 pipe
+__device__ __forceinline__ bool is_finite(double x) { return (__double2hiint(x) & 0x7ff00000) != 0x7ff00000; }
 
 }  // namespace bambu
