@@ -141,9 +141,11 @@ __host__ __device__ inline SellLayout sell_layout(uint32_t M, uint32_t NL, uint3
 // vector region of the EM kernel: theta[M+1] | ratio[NL+1]
 __host__ __device__ inline uint32_t sell_vec_bytes(uint32_t M, uint32_t NL) { return align_up(8u * (M + NL + 2), 16); }
 
+constexpr uint32_t kSellFlagBytes = 16;   // per-update flag words in front of the vectors
+
 __host__ __device__ inline uint32_t sell_smem_bytes(const SellLayout &L, uint32_t M, uint32_t NL)
 {
-    return sell_vec_bytes(M, NL) + L.copy_bytes;
+    return kSellFlagBytes + sell_vec_bytes(M, NL) + L.copy_bytes;
 }
 
 // shared-memory scratch of the SELL builder for a group (lengths, ids, slice starts, histogram)

@@ -10,7 +10,7 @@
 // one live column in the E-phase and one row in the M-phase; a warp owns slices of 32;
 // a CTA owns one group at a time and pulls groups from its class's queue.
 //
-// Shared memory: [theta f64 M+1][ratio f64 NL+1][image].  Both vectors and the per-line constants
+// Shared memory: [flag words 16 B][theta f64 M+1][ratio f64 NL+1][image].  Both vectors and the per-line constants
 // (rs, Y) are stored BY POSITION (32*slice + lane), so a lane's own line needs no index lookup, and
 // the image stores every gathered index as the byte offset of the element in that vector region, so
 // a gather needs no address arithmetic.  theta[M] and ratio[NL] are always 0.0: padding entries
@@ -100,8 +100,12 @@ em_sell_kernel(const int32_t *__restrict__ queue, const int *__restrict__ qcount
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int s_next;
-    __shared__ int s_nf[2];    // rows whose theta is non-finite, written by M-phase `it` into [it&1]
-    __shared__ int s_rbad[2];  // a ratio Y/c of E-phase `it` is non-finite, [it&1]
+    // The per-update flag words sit in the first 16 bytes of the dynamic shared memory, whose base the kernel
+    // keeps in a register anyway (as static __shared__ symbols their addresses were rebuilt every update):
+    //   s_nf[2]:   rows whose theta is non-finite, written by M-phase `it` into [it&1]
+    //   s_rbad[2]: a ratio Y/c of E-phase `it` is non-finite, [it&1]
+    int *const s_nf = reinterpret_cast<int *>(smem);
+    int *const s_rbad = s_nf + 2;
     __shared__ int s_Q;        // columns whose baseSum is +-inf (epilogue)
     __shared__ __align__(8) uint64_t s_mbar;   // completion of the image's bulk copy
     uint32_t load_parity = 0;
@@ -129,8 +133,8 @@ em_sell_kernel(const int32_t *__restrict__ queue, const int *__restrict__ qcount
         const int64_t row0 = grp_row_ptr[g];
 
         const uint32_t vec_bytes = sell_vec_bytes((uint32_t)M, (uint32_t)NL);
-        const uint8_t *vec = smem;                       // theta[M+1] | ratio[NL+1]
-        uint8_t *simg = smem + vec_bytes;
+        const uint8_t *vec = smem + kSellFlagBytes;      // theta[M+1] | ratio[NL+1]
+        uint8_t *simg = smem + kSellFlagBytes + vec_bytes;
 
         // ---- image -> shared memory ------------------------------------------------
         if (kTma) {
@@ -154,7 +158,7 @@ em_sell_kernel(const int32_t *__restrict__ queue, const int *__restrict__ qcount
         const uint8_t *sideC = simg + L.sideC;
         const uint2 *descR = reinterpret_cast<const uint2 *>(simg + L.descR);
         const uint2 *descC = reinterpret_cast<const uint2 *>(simg + L.descC);
-        double *theta = reinterpret_cast<double *>(smem);                   // M + 1, theta[M] = 0 (padding target)
+        double *theta = reinterpret_cast<double *>(smem + kSellFlagBytes);  // M + 1, theta[M] = 0 (padding target)
         double *ratio = theta + (M + 1);                                    // NL + 1, ratio[NL] = 0
         for (int i = tid; i < M; i += T) theta[i] = 1.0;                    // src/em.cpp:20-21
         if (tid == 0) {
