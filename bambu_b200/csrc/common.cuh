@@ -238,4 +238,23 @@ __device__ __forceinline__ void sort_column(IdxT *idx, double *val, uint32_t lo,
 // exponent field not all ones; an integer test on the high word keeps it off the FP64 pipe
 __device__ __forceinline__ bool is_finite(double x) { return (__double2hiint(x) & 0x7ff00000) != 0x7ff00000; }
 
+// num / den, correctly rounded like __ddiv_rn, for the M-phase's theta' = sum / rs.
+// The library division leaves its fast path when the numerator is below 2^-969 (or zero): thetas that have
+// decayed that far are common late in long runs and each one stalls its warp for ~450 cycles.  Such a numerator
+// is scaled by 2^960 first (exact) and the quotient scaled back (exact while it stays a normal number); zero is
+// passed through; everything else -- subnormal quotients, den = 0, NaN -- still goes to the real division.
+__device__ __forceinline__ double div_small_numerator(double num, double den)
+{
+    const bool tiny = (__double2hiint(num) & 0x7fffffff) < 0x03700000;      // |num| < 2^-968
+    double top = num;
+    if (tiny) top = (num == 0.0) ? 1.0 : __dmul_rn(num, 0x1p960);
+    double q = __ddiv_rn(top, den);
+    if (tiny) {
+        if (num == 0.0) q = (den > 0.0) ? num : __ddiv_rn(num, den);
+        else if (fabs(q) >= 0x1p-61 && fabs(q) <= 1.7976931348623157e308) q = __dmul_rn(q, 0x1p-960);
+        else q = __ddiv_rn(num, den);
+    }
+    return q;
+}
+
 }  // namespace bambu

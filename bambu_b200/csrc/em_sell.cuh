@@ -240,22 +240,7 @@ em_sell_kernel(const int32_t *__restrict__ queue, const int *__restrict__ qcount
                 bool inband = false;
                 double after = 0.0, diff = 0.0;
                 if (i < M) {
-                    // The library division leaves its fast path when the numerator is below 2^-969 (or zero):
-                    // thetas that have decayed that far are common late in long runs and each one stalls its warp
-                    // for ~450 cycles.  Such a numerator is scaled by 2^960 first (exact) and the quotient scaled
-                    // back (exact while it stays a normal number), zero is passed through; everything else --
-                    // subnormal quotients, rs = 0, NaN -- still goes to the real division.
-                    const double num = __dadd_rn(a1, a2), den = rs[i];
-                    const bool tiny = (__double2hiint(num) & 0x7fffffff) < 0x03700000;      // |num| < 2^-968
-                    double top = num;
-                    if (tiny) top = (num == 0.0) ? 1.0 : __dmul_rn(num, 0x1p960);
-                    after = __ddiv_rn(top, den);
-                    if (tiny) {
-                        if (num == 0.0) after = (den > 0.0) ? num : __ddiv_rn(num, den);
-                        else if (fabs(after) >= 0x1p-61 && fabs(after) <= 1.7976931348623157e308)
-                            after = __dmul_rn(after, 0x1p-960);
-                        else after = __ddiv_rn(num, den);
-                    }
+                    after = div_small_numerator(__dadd_rn(a1, a2), rs[i]);     // == __ddiv_rn, see common.cuh
                     theta[i] = after;
                     if (!is_finite(after)) atomicAdd(&s_nf[par], 1);
                     if (after > P.minvalue) {

@@ -448,7 +448,7 @@ em_giant_kernel(const GiantDesc *__restrict__ descs, int n_giant, const uint8_t 
                 double sA, sB;
                 if (hazard) row_streams<true>(cidx, cval, loA, hiA, hiA, hiB, lane, th, ratio, stage, sA, sB);
                 else row_streams<false>(cidx, cval, loA, hiA, hiA, hiB, lane, th, ratio, stage, sA, sB);
-                const double after = __ddiv_rn(__dadd_rn(sA, sB), rs[i]);     // every lane: same value
+                const double after = div_small_numerator(__dadd_rn(sA, sB), rs[i]);     // == __ddiv_rn; every lane: same value
                 bool inband = false;
                 double diff = 0.0;
                 int flag = (P.conv < 0.0) ? 1 : 0;
