@@ -106,16 +106,18 @@ struct EmClass {
     uint32_t max_bytes;   // dynamic shared memory of the class
     int threads;
 };
-// An SM has 228 KB of shared memory and every resident CTA costs 1 KB of it on top of its dynamic size, so
-// k CTAs fit when the class size is at most 233472 / k - 1024.  Registers cap the 64-thread kernel at 16 CTAs
-// (64 registers) and the 128-thread kernel at 9 (56 registers).  Measured on a config-4 sample, weighted by
-// EM updates: 77 % of the work is in groups of at most 13.25 KB, 19 % between that and 24 KB (tools/image_sizes.py).
+// An SM has 228 KB (233472 B) of shared memory; a resident CTA costs its dynamic size plus the kernel's static
+// shared memory (16 B), rounded up to 128 B, plus 1 KB of system use.  k CTAs fit when the class size is at most
+// floor128(233472 / k - 1024 - 128).  Registers cap the 64-thread kernel at 16 CTAs (64 registers) and the
+// 128-thread kernel at 9 (56 registers).  Measured on a config-4 sample, weighted by EM updates: ~77 % of the work is
+// in groups of at most 13 KB, ~19 % between that and 24 KB (tools/image_sizes.py).  bench.py / ncu show the result as
+// launch__occupancy_limit_shared_mem.
 static const EmClass kEmClasses[kNumClasses] = {
-    {6272u, 64},           // 233472/32 - 1024 (the CTA limit; the register file stops at 16)
-    {13568u, 64},          // 16 CTAs/SM
-    {24912u, 128},         // 9
-    {57344u, 256},         // 4
-    {115712u, 512},        // 2
+    {6144u, 64},           // 32 would fit (the CTA limit); the register file stops at 16
+    {13440u, 64},          // 16 CTAs/SM
+    {24704u, 128},         // 9
+    {57216u, 256},         // 4
+    {115584u, 512},        // 2
     {kSmemMax, 1024},      // 1
 };
 static int g_em_grid[kNumClasses] = {};
