@@ -370,11 +370,11 @@ def run_b200(args):
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         # DRAM bytes of the dominant kernel (em_sell_kernel<64>, 13.25 KB class) per launch, from the
-                         # ncu capture profiles/r1_ncu_per_bucket.txt: 151.5 MB for a 4-sample slab, scaled to this slab
-                         "traffic": 151.48e6 / 4.0 * args.samples * args.scale,
-                         "traffic_note": "dram__bytes_read+write of em_sell_kernel<64> (13.25 KB class): 37.9 MB per sample "
-                                         "(profiles/r1_ncu_per_bucket.txt), i.e. the group images are read once; "
+                         # DRAM bytes of the dominant kernel (em_sell_kernel<64>, 13 KB class) per launch, from the ncu
+                         # --set full capture profiles/r1_v4_em_sell_metrics.txt: 147.9 MB for a 4-sample slab, scaled
+                         "traffic": 147.92e6 / 4.0 * args.samples * args.scale,
+                         "traffic_note": "dram__bytes_read+write of em_sell_kernel<64> (13 KB class): 37.0 MB per sample "
+                                         "(profiles/r1_v4_em_sell_metrics.txt), i.e. the group images are read once; "
                                          "the 24 B x nnz x iters of 'achieved' never leave shared memory",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "kernel": "em_sell_kernel (all size classes; pack + SELL kernels included in the time)",
