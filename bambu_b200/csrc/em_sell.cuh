@@ -204,7 +204,11 @@ em_sell_kernel(const int32_t *__restrict__ queue, const int *__restrict__ qcount
             const bool hazard = (s_rbad[par] != 0) || (nP != 0);
             if (tid == 0) s_rbad[par ^ 1] = 0;
             int flag = (P.conv < 0.0) ? 1 : 0;   // delta >= 0 > conv whenever conv is negative
-            for (int sl = warp; sl < nSliceR; sl += NW) {
+            // slices are sorted by line length: deal them to the warps in snake order (w0 w1 | w1 w0 | ...) so that
+            // the warp that got the longest slice gets the shortest of the next pass
+            for (int base = 0; base < nSliceR; base += NW) {
+                const int sl = base + (((base / NW) & 1) ? NW - 1 - warp : warp);
+                if (sl >= nSliceR) continue;
                 const int i = sl * 32 + lane;        // the lane's row, by position
                 const double th = theta[min(i, M)];  // padding lanes read theta[M] = 0.0
                 double a1 = 0.0, a2 = 0.0;
