@@ -101,6 +101,17 @@ class EmPlan:
                                                 _ptr(self._r)))
         self._keep = None
 
+    def reset(self, arena: Arena):
+        """Re-analyse another arena in this plan (``bambu_em_plan_reset``): device buffers are kept and only grow.
+        The payload has to be uploaded / bound again."""
+        self.arena = arena
+        self._g = _c(arena.grp_row_ptr, np.int64)
+        self._c = _c(arena.grp_col_ptr, np.int64)
+        self._r = _c(arena.row_nnz_ptr, np.int64)
+        self.n_groups, self.rows = len(self._g) - 1, int(self._g[-1])
+        _lib.check(self._L.bambu_em_plan_reset(self._h, self.n_groups, _ptr(self._g), _ptr(self._c), _ptr(self._r)))
+        self._keep = None
+
     def set_stream(self, cuda_stream: int | None):
         _lib.check(self._L.bambu_em_plan_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
 

@@ -340,3 +340,28 @@ def test_long_shared_columns(em, oracle_mod):
                      (np.bincount(c, minlength=N) > 1).astype(np.uint8), np.arange(M, dtype=np.int32))
     a = Arena.concatenate([locus(2000, 2, 2100), locus(3000, 12, 4000), random_arena(rng, n_groups=4)])
     check_against_oracle(em, oracle_mod, a, maxiter=120)
+
+
+@pytest.mark.gpu
+def test_plan_reset_reuses_the_plan(em, oracle_mod):
+    """bambu_em_plan_reset: differently shaped arenas through one plan (grow-only device buffers), each identical to
+    the oracle; running before the payload is there again is a state error."""
+    from bambu_b200.em import EmPlan
+    from bambu_b200 import synthetic, _lib
+    arenas = [synthetic.config2(scale=0.01), synthetic.config2(seed=11, scale=0.03), synthetic.config2(seed=12, scale=0.005)]
+    with EmPlan(arenas[0]) as plan:
+        sizes = []
+        for k, a in enumerate(arenas):
+            if k:
+                plan.reset(a)
+                with pytest.raises(_lib.BambuEmError) as e:
+                    plan.run()
+                assert e.value.code == _lib.ESTATE
+            plan.upload()
+            plan.run(maxiter=10000, minvalue=1e-8, conv=1e-2)
+            est, iters, status = plan.download()
+            o_est, o_it, o_st = oracle_mod.em_batched(a, maxiter=10000, minvalue=1e-8, conv=1e-2, mode=oracle_mod.MODE_SPARSE)
+            assert np.array_equal(iters, o_it) and np.array_equal(status, o_st)
+            assert_same_doubles(est, o_est, f"arena {k}")
+            sizes.append(plan.device_bytes())
+        assert sizes[1] >= sizes[0] and sizes[2] == sizes[1]      # buffers grow, never shrink
