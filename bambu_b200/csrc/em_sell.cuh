@@ -22,7 +22,7 @@
 #include "common.cuh"
 
 #ifndef BAMBU_V_UNROLL
-#define BAMBU_V_UNROLL 2
+#define BAMBU_V_UNROLL 1
 #endif
 
 namespace bambu {
