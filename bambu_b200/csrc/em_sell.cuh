@@ -111,7 +111,7 @@ em_sell_kernel(const int32_t *__restrict__ queue, const int *__restrict__ qcount
     uint32_t load_parity = 0;
 
     constexpr int NW = T / 32;
-    // large slices (classes of 28 KB and up) come in by TMA bulk copy; for the ~11 KB images of the
+    // large slices (classes of 24 KB and up) come in by TMA bulk copy; for the ~11 KB images of the
     // small classes a cooperative 16-byte load loop measured ~3 % faster (no mbarrier round trip)
     constexpr bool kTma = (T >= 128);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
