@@ -115,3 +115,30 @@ def test_genEquiRCs_chr9(oracle_mod):
     got = A.quantify_assays(quant, fx["annotation"]["txid"], inc)
     for name in ("counts", "CPM", "fullLengthCounts", "uniqueCounts"):
         assert_same_doubles(got[name], np.array(fx["expected_assays"][name], dtype=np.float64), name)
+
+
+def test_duplicated_sample_chain(gene_cases, oracle_mod):
+    """tests/testthat/test_quant.R:63-66 / test_transcriptToGeneExpression.R:18-21: the same sample twice, from the distance
+    table to the gene level -- genEquiRCs -> bambu.quantDT -> quantify_assays -> combine_assays reproduces the counts
+    stored in seOutputCombined_*.rds, and transcriptToGeneExpression on them gives seCombinedGeneExpected."""
+    from bambu_b200.equirc import AnnotationClasses, genEquiRCs
+    from bambu_b200.quantify import bambu_quantDT
+    with open(os.path.join(GOLDEN, "chr9_e2e.json")) as f:
+        fx = json.load(f)
+    ann = AnnotationClasses(fx["annotation"])
+    inc = [np.nan if v is None else v for v in fx["incompatibleCounts"]["counts"]]
+    one = []
+    for _ in range(2):
+        quant = bambu_quantDT(genEquiRCs(fx["distTable"], fx["readClasses"], ann), {"degradationBias": True},
+                              em=lambda a, maxiter, conv, minvalue: oracle_mod.em_batched(a, maxiter=maxiter, conv=conv,
+                                                                                          minvalue=minvalue))
+        one.append(A.quantify_assays(quant, fx["annotation"]["txid"], inc))
+    combined = gene_cases[2]
+    assays, _ = A.combine_assays(one, combined["input"]["sample_names"])
+    assert_same_doubles(assays["counts"], _mat(combined["input"]["counts"], combined["input"]["dim"]), "combined counts")
+    genes, names, cg, cpm = A.transcriptToGeneExpression(assays["counts"], fx["annotation"]["GENEID"],
+                                                         combined["input"]["sample_names"], combined["input"]["incompatibleCounts"])
+    e = combined["expected"]
+    assert genes == e["GENEID"] and names == e["sample_names"]
+    assert_same_doubles(cg, _mat(e["counts"], e["dim"]), "gene counts")
+    assert_same_doubles(cpm, _mat(e["CPM"], e["dim"]), "gene CPM")
