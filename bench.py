@@ -118,7 +118,27 @@ def cpu_reference(arena, mode, steps, warmup, threads=0):
         if i >= warmup:
             best.append(dt)
     work = float((nz * iters).sum())
+    cpu_reference.last = (est, iters, status)
     return work, float(np.sum(best)), oracle.num_threads() if threads <= 0 else threads
+
+
+def parity_block(arena, groups, gpu, cpu):
+    """Whole-table comparison (tests/testthat/test_quant.R:12-27 style) of the GPU results for ``groups`` of ``arena``
+    with the oracle's on the sub-arena of exactly those groups.  ``gpu`` / ``cpu``: (est[3, rows], iters, status)."""
+    M = np.diff(arena.grp_row_ptr)[groups]
+    starts = arena.grp_row_ptr[groups]
+    rows = np.repeat(starts - np.concatenate(([0], np.cumsum(M)[:-1])), M) + np.arange(int(M.sum()))
+    g_est, g_it, g_st = gpu[0][:, rows], gpu[1][groups], gpu[2][groups]
+    c_est, c_it, c_st = cpu
+    nan_same = bool(np.array_equal(np.isnan(g_est), np.isnan(c_est)))
+    a, b = np.nan_to_num(g_est, nan=0.0), np.nan_to_num(c_est, nan=0.0)
+    ndiff = int(np.count_nonzero(a.view(np.int64) != b.view(np.int64)))
+    den = np.maximum(np.abs(b), 1e-300)
+    max_rel = float(np.max(np.abs(a - b) / den)) if a.size else 0.0
+    return {"groups": int(len(groups)), "rows": int(len(rows)), "iters_equal": bool(np.array_equal(g_it, c_it)),
+            "status_equal": bool(np.array_equal(g_st, c_st)), "doubles_equal": bool(nan_same and ndiff == 0),
+            "doubles_differing": ndiff, "max_rel": max_rel,
+            "against": "oracle/em_oracle.c sparse mode on the same groups of cohort sample 0 (CPU)"}
 
 
 def bounded_cpu_sample(scale, frac, seed=0):
@@ -390,10 +410,15 @@ def run_b200(args):
         if world == 1 and not args.no_cpu:
             import oracle
             oracle.build()
-            sub = arena.select_groups(np.sort(np.random.default_rng(0).choice(
-                int(arena.sample_grp_ptr[1]), max(1, int(arena.sample_grp_ptr[1] / args.cpu_frac)), replace=False)))
+            sel = np.sort(np.random.default_rng(0).choice(
+                int(arena.sample_grp_ptr[1]), max(1, int(arena.sample_grp_ptr[1] / args.cpu_frac)), replace=False))
+            sub = arena.select_groups(sel)
             w1, s1, cores = cpu_reference(sub, oracle.MODE_DENSE_TRACE, 1, 0, threads=os.cpu_count() or 1)
             w2, s2, _ = cpu_reference(sub, oracle.MODE_SPARSE, 3, 1, threads=os.cpu_count() or 1)
+            # the oracle as the checker: the e2e run's tables for these groups must be the oracle's, double for double
+            line["parity"] = parity_block(arena, sel, (h_est.numpy(), h_iters.numpy()[:n_groups], h_status.numpy()[:n_groups]),
+                                          cpu_reference.last)
+            parity_ok = line["parity"]["iters_equal"] and line["parity"]["status_equal"] and line["parity"]["doubles_equal"]
             line["cpu_baseline"] = {
                 "value": w1 / s1, "unit": "nnz-iterations/s", "cores": cores, "kind": "port",
                 "sample": f"{sub.n_groups} of the {int(arena.sample_grp_ptr[1])} gene groups of cohort sample 0 "
@@ -404,6 +429,8 @@ def run_b200(args):
         if world == 1 and not args.no_stage:
             line["quantDT_stage"] = quantdt_stage(args)
         print(json.dumps(line))
+        if world == 1 and not args.no_cpu and not parity_ok:
+            raise SystemExit("bench: GPU results differ from the oracle on cohort sample 0 (see 'parity')")
     plan.close()
     if world > 1:
         dist.destroy_process_group()

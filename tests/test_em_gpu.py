@@ -109,6 +109,40 @@ def test_config2_full_size(em, oracle_mod):
     assert np.all(est >= 0)
 
 
+def test_config4_cohort_slab(em, oracle_mod):
+    """BASELINE.json configs[3] -- the workload bench.py times: a slab of cohort samples (shared annotation, per-sample
+    counts, 20 % of the multi-transcript classes re-drawn, per-sample degradation rate) at full sample size.  Whole-table
+    equality with the sparse oracle, like tests/testthat/test_quant.R:12-27: identical doubles and iteration counts."""
+    from bambu_b200 import synthetic
+    from bambu_b200.arena import Arena
+    ann = synthetic.annotation_for("config4")
+    samples = [synthetic.cohort_sample(ann, s) for s in (0, 1, 7)]
+    rates = [x.meta["d_rate"] for x in samples]
+    assert len(set(rates)) == 3 and max(rates) - min(rates) > 0.02          # different per-sample d_rate
+    a = Arena.concatenate(samples)
+    assert a.nnz > 5_500_000 and a.n_rows == 3 * 250_000
+    est, iters, status = check_against_oracle(em, oracle_mod, a)
+    assert (status == 0).all() and iters.max() > 500
+    # sample s of the slab == the sample on its own (groups do not interact, R/bambu.R:187)
+    one = em.abundance_quantification(samples[1], maxiter=10000)
+    r0, r1 = samples[0].n_rows, samples[0].n_rows + samples[1].n_rows
+    assert_same_doubles(est[:, r0:r1], one[0], "sample 1 inside the slab vs alone")
+
+
+def test_config5_cohort_sample(em, oracle_mod):
+    """BASELINE.json configs[4] shape: 75k genes / 400k transcripts / 800k read classes / ~3.2M entries, one sample."""
+    from bambu_b200 import synthetic
+    ann = synthetic.annotation_for("config5")
+    a = synthetic.cohort_sample(ann, 3)
+    assert a.n_rows == 400_000 and a.n_cols == 800_000 and a.nnz > 3_000_000
+    est, iters, status = check_against_oracle(em, oracle_mod, a)
+    assert (status == 0).all()
+    M, N, _ = a.group_shapes()
+    got = np.bincount(np.repeat(np.arange(a.n_groups), M), weights=est[0], minlength=a.n_groups)
+    want = np.bincount(np.repeat(np.arange(a.n_groups), N), weights=a.K * a.Y, minlength=a.n_groups)
+    assert np.allclose(got, want, rtol=1e-9)
+
+
 def test_emWithL1_dense_entry(em, oracle_mod):
     rng = np.random.default_rng(3)
     for M, N in ((3, 4), (1, 5), (7, 20), (30, 64)):
@@ -272,8 +306,12 @@ def test_config3_scaled(em, oracle_mod):
     ann = synthetic.annotation_for("config3", scale=0.04)      # 200 genes incl. 2 giant loci
     a = synthetic.sample_arena(ann, 0)
     M, N, e = a.group_shapes()
-    assert e.max() > 1_000_000
+    # the two giant loci have their FULL size (2-4k transcripts x 100-200k read classes, millions of entries each);
+    # only the number of loci and of ordinary genes is scaled, and maxiter bounds the oracle's run time
+    big = np.argsort(e)[-2:]
+    assert (M[big] >= 2000).all() and (N[big] >= 100_000).all() and (e[big] > 1_000_000).all()
     est, iters, status = check_against_oracle(em, oracle_mod, a, maxiter=150)
+    assert (iters[big] == 149).all()
     got = np.bincount(np.repeat(np.arange(a.n_groups), M), weights=est[0], minlength=a.n_groups)
     want = np.bincount(np.repeat(np.arange(a.n_groups), N), weights=a.K * a.Y, minlength=a.n_groups)
     assert np.allclose(got, want, rtol=1e-9)
