@@ -24,6 +24,14 @@ SYMBOLS = {
     "bambu_em_set_device": (ctypes.c_int, [ctypes.c_int]),
     "bambu_em_shutdown": (ctypes.c_int, []),
     "bambu_em_batched": (ctypes.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _f64, _f64, _p, _p, _p]),
+    "bambu_em_batched_v2": (ctypes.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _i32, _f64, _f64, _p, _p, _p]),
+    "bambu_wire_last_error": (ctypes.c_char_p, []),
+    "bambu_wire_create": (ctypes.c_int, [ctypes.POINTER(_p), _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "bambu_wire_free": (ctypes.c_int, [_p]),
+    "bambu_wire_sizes": (ctypes.c_int, [_p] + [ctypes.POINTER(_i64)] * 5 + [ctypes.POINTER(_i32), ctypes.POINTER(_i64)]),
+    "bambu_wire_arrays": (ctypes.c_int, [_p] + [ctypes.POINTER(_p)] * 12),
+    "bambu_em_plan_create_v2": (ctypes.c_int, [ctypes.POINTER(_p), _i64, _p, _p, _p]),
+    "bambu_em_plan_upload_v2": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _i32, _p, _p, _p]),
     "bambu_emWithL1": (ctypes.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _f64, _f64, _p, _p]),
     "bambu_em_plan_create": (ctypes.c_int, [ctypes.POINTER(_p), _i64, _p, _p, _p]),
     "bambu_em_plan_reset": (ctypes.c_int, [_p, _i64, _p, _p, _p]),

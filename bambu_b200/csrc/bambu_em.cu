@@ -71,7 +71,7 @@ static int ensure_device()
     if (g_device >= n) return fail(BAMBU_EM_ENODEVICE, "device %d requested, %d present", g_device, n);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, g_device));
-    if (prop.major != 10)
+    if (prop.major != 10 || prop.minor != 0)     // an arch-specific ("a") cubin runs on exactly this compute capability
         return fail(BAMBU_EM_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
                     g_device, prop.major, prop.minor);
     CUDA_TRY(cudaSetDevice(g_device));
@@ -194,9 +194,14 @@ struct Slot {
     int64_t cols() const { return c1 - c0; }
     int64_t nnz() const { return e1 - e0; }
     bool single_tx_shortcut = true;   // R/bambu-quantify_utilityFunctions.R:410-414 (run_parallel, not emWithL1)
+    // wire form v2 (bambu_em_batched_v2): columns = live columns, entries = live entries, [ib0, ib1) = the range's
+    // bytes of the caller's index blob
+    bool v2 = false;
+    int64_t ib0 = 0, ib1 = 0;
+    int32_t col_mode = 0;
     // device buffers (grow-only)
     DevBuf grp_row_ptr, grp_col_ptr, row_nnz_ptr, payload, img, img_off, info, pool, ginfo, queue, nnz_nonzero, est,
-        iters, status, work, ctrl, gdesc, gbuf;
+        iters, status, work, ctrl, gdesc, gbuf, grp_idx_off;
     // per-group extents of the current chunk (host copy: the caller's arrays may be gone by the time a
     // group has to be moved to the streamed tier)
     std::vector<int32_t> hM, hN;
@@ -218,8 +223,12 @@ struct Slot {
     const uint8_t *v_nz_flags = nullptr;
     const double *v_Y = nullptr, *v_K = nullptr;
     const uint8_t *v_col_flags = nullptr;
+    // the same for the wire form v2
+    const uint32_t *w_row_end = nullptr, *w_eq_bits = nullptr, *w_multi_bits = nullptr;
+    const double *w_rs = nullptr, *w_aval = nullptr;
+    const uint8_t *w_cidx = nullptr, *w_colY = nullptr, *w_colK = nullptr;
     // host staging (pinned): img_off + work lists of the current chunk
-    PinBuf h_img_off, h_work;
+    PinBuf h_img_off, h_work, h_idx_off;
     Bucket buckets[8];
     int n_single = 0;
     int32_t *d_single = nullptr;
@@ -278,8 +287,10 @@ static void slot_destroy(Slot &s)
         if (e) cudaEventDestroy(e);
     if (s.own_stream) cudaStreamDestroy(s.own_stream);
     for (DevBuf *b : {&s.grp_row_ptr, &s.grp_col_ptr, &s.row_nnz_ptr, &s.payload, &s.img, &s.img_off, &s.info, &s.pool,
-                      &s.ginfo, &s.queue, &s.nnz_nonzero, &s.est, &s.iters, &s.status, &s.work, &s.ctrl, &s.gdesc, &s.gbuf})
+                      &s.ginfo, &s.queue, &s.nnz_nonzero, &s.est, &s.iters, &s.status, &s.work, &s.ctrl, &s.gdesc, &s.gbuf,
+                      &s.grp_idx_off})
         b->release();
+    s.h_idx_off.release();
     s.h_gdesc.release();
     s.h_img_off.release();
     s.h_work.release();
@@ -313,6 +324,7 @@ template <int T>
 static int pack_config_T()
 {
     CUDA_TRY(cudaFuncSetAttribute(pack_resident_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    CUDA_TRY(cudaFuncSetAttribute(pack_resident_wire_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     CUDA_TRY(cudaFuncSetAttribute(sell_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     return BAMBU_EM_OK;
 }
@@ -349,6 +361,7 @@ static int configure_kernels()
 
 struct SlotViews {   // device pointers shifted so that absolute group / row / column / entry indices work
     ArenaDev A;
+    WireDev W;
     const int64_t *img_off;
     PackInfo *info;
     GroupImg *ginfo;
@@ -368,6 +381,14 @@ static SlotViews slot_views(const Slot &s)
     v.A.Y = s.v_Y; v.A.K = s.v_K; v.A.col_flags = s.v_col_flags;
     v.A.n_groups = s.ng();
     v.A.total_rows = s.rows();
+    v.W.grp_row_ptr = v.A.grp_row_ptr;
+    v.W.grp_col_ptr = v.A.grp_col_ptr;
+    v.W.grp_ent_ptr = s.row_nnz_ptr.as<int64_t>() - s.g0;       // v2 keeps the per-group entry pointers in this buffer
+    v.W.grp_idx_off = s.grp_idx_off.as<int64_t>() - s.g0;
+    v.W.row_end = s.w_row_end; v.W.rs = s.w_rs; v.W.aval = s.w_aval; v.W.cidx = s.w_cidx; v.W.eq_bits = s.w_eq_bits;
+    v.W.colY = s.w_colY; v.W.colK = s.w_colK; v.W.multi_bits = s.w_multi_bits; v.W.col_mode = s.col_mode;
+    v.W.n_groups = s.ng();
+    v.W.total_rows = s.rows();
     v.img_off = s.img_off.as<int64_t>() - s.g0;
     v.info = s.info.as<PackInfo>() - s.g0;
     v.ginfo = s.ginfo.as<GroupImg>() - s.g0;
@@ -382,9 +403,14 @@ static SlotViews slot_views(const Slot &s)
 template <int T>
 static int launch_pack_T(Slot &s, Bucket &b, const SlotViews &v)
 {
-    pack_resident_kernel<T><<<b.n, T, b.smem_pack, b.stream>>>(v.A, b.d_work, b.n, v.img_off, s.img.as<uint8_t>(), v.info,
-                                                                v.nnz_nonzero, v.est, v.status, &v.ctrl->err,
-                                                                s.single_tx_shortcut ? 1 : 0);
+    if (s.v2)
+        pack_resident_wire_kernel<T><<<b.n, T, b.smem_pack, b.stream>>>(v.W, b.d_work, b.n, v.img_off, s.img.as<uint8_t>(),
+                                                                         v.info, v.nnz_nonzero, v.est, v.status, &v.ctrl->err,
+                                                                         s.single_tx_shortcut ? 1 : 0);
+    else
+        pack_resident_kernel<T><<<b.n, T, b.smem_pack, b.stream>>>(v.A, b.d_work, b.n, v.img_off, s.img.as<uint8_t>(), v.info,
+                                                                    v.nnz_nonzero, v.est, v.status, &v.ctrl->err,
+                                                                    s.single_tx_shortcut ? 1 : 0);
     CUDA_TRY(cudaGetLastError());
     sell_kernel<T><<<b.n, T, b.smem_sell, b.stream>>>(b.d_work, b.n, v.A.grp_row_ptr, v.img_off, s.img.as<uint8_t>(), v.info,
                                                        s.pool.as<uint8_t>(), (unsigned long long)s.pool_bytes,
@@ -433,20 +459,31 @@ static int launch_em(Slot &s, int c, const SlotViews &v)
 // ------------------------------------------------------------------------------
 // slot_prepare: host-side analysis of the range [g0, g1) + upload of its structure
 // ------------------------------------------------------------------------------
-// grp_row_ptr / grp_col_ptr / row_nnz_ptr are the caller's HOST arrays of the whole arena.
+// grp_row_ptr / grp_col_ptr / row_nnz_ptr are the caller's HOST arrays of the whole arena.  Wire form v2
+// (grp_ent_ptr != NULL): columns and entries are the live ones, row_nnz_ptr is not used, idx_byte0 is the offset of
+// group g0's index block in the caller's blob.
 static int slot_prepare(Slot &s, const int64_t *grp_row_ptr, const int64_t *grp_col_ptr, const int64_t *row_nnz_ptr,
-                        int64_t g0, int64_t g1)
+                        int64_t g0, int64_t g1, const int64_t *grp_ent_ptr = nullptr, int64_t idx_byte0 = 0)
 {
     TRY(slot_init(s));
     TRY(configure_kernels());
+    s.v2 = (grp_ent_ptr != nullptr);
     s.g0 = g0; s.g1 = g1;
     s.r0 = grp_row_ptr[g0]; s.r1 = grp_row_ptr[g1];
     s.c0 = grp_col_ptr[g0]; s.c1 = grp_col_ptr[g1];
-    s.e0 = row_nnz_ptr[s.r0]; s.e1 = row_nnz_ptr[s.r1];
+    if (s.v2) { s.e0 = grp_ent_ptr[g0]; s.e1 = grp_ent_ptr[g1]; }
+    else { s.e0 = row_nnz_ptr[s.r0]; s.e1 = row_nnz_ptr[s.r1]; }
     const int64_t ng = s.ng();
     if (ng > INT32_MAX / kNumClasses) return fail(BAMBU_EM_EINVAL, "too many groups in one chunk");
-    for (int64_t r = s.r0; r < s.r1; ++r)
-        if (row_nnz_ptr[r + 1] < row_nnz_ptr[r]) return fail(BAMBU_EM_EINVAL, "row_nnz_ptr decreases at row %lld", (long long)r);
+    if (!s.v2)
+        for (int64_t r = s.r0; r < s.r1; ++r)
+            if (row_nnz_ptr[r + 1] < row_nnz_ptr[r]) return fail(BAMBU_EM_EINVAL, "row_nnz_ptr decreases at row %lld", (long long)r);
+    int64_t *idx_off = nullptr;
+    int64_t ib = idx_byte0;
+    if (s.v2) {
+        TRY(s.h_idx_off.ensure(sizeof(int64_t) * (size_t)(ng + 1)));
+        idx_off = s.h_idx_off.as<int64_t>();
+    }
 
     // ---- classify by worst-case footprint, lay out the stage-1 images ---------------
     TRY(s.h_img_off.ensure(sizeof(int64_t) * (size_t)(ng + 1)));
@@ -465,7 +502,14 @@ static int slot_prepare(Slot &s, const int64_t *grp_row_ptr, const int64_t *grp_
     for (int64_t g = g0; g < g1; ++g) {
         const int64_t M = grp_row_ptr[g + 1] - grp_row_ptr[g], N = grp_col_ptr[g + 1] - grp_col_ptr[g];
         if (M < 0 || N < 0) return fail(BAMBU_EM_EINVAL, "group %lld has negative extent", (long long)g);
-        const int64_t e = row_nnz_ptr[grp_row_ptr[g + 1]] - row_nnz_ptr[grp_row_ptr[g]];
+        const int64_t e = s.v2 ? grp_ent_ptr[g + 1] - grp_ent_ptr[g]
+                               : row_nnz_ptr[grp_row_ptr[g + 1]] - row_nnz_ptr[grp_row_ptr[g]];
+        if (e < 0) return fail(BAMBU_EM_EINVAL, "group %lld has a negative entry count", (long long)g);
+        if (s.v2) {     // index blocks: 4-byte aligned, u16 per entry while the live column index fits 15 bits
+            ib = (ib + 3) / 4 * 4;
+            idx_off[g - g0] = ib;
+            ib += e * wire_idx_width(N);
+        }
         gnnz[g - g0] = e;
         img_off[g - g0] = off;
         s.hM[g - g0] = (int32_t)std::min<int64_t>(M, INT32_MAX); s.hN[g - g0] = (int32_t)std::min<int64_t>(N, INT32_MAX); s.hE[g - g0] = e;
@@ -496,6 +540,7 @@ static int slot_prepare(Slot &s, const int64_t *grp_row_ptr, const int64_t *grp_
         off += img_layout((uint32_t)M, (uint32_t)N, (uint32_t)e).total;
     }
     img_off[ng] = off;
+    if (s.v2) { idx_off[ng] = ib; s.ib0 = idx_byte0; s.ib1 = ib; }
 
     // work lists: per pack class, largest groups first (they are queued for the EM first)
     int32_t *work = s.h_work.as<int32_t>();
@@ -525,7 +570,8 @@ static int slot_prepare(Slot &s, const int64_t *grp_row_ptr, const int64_t *grp_
     s.pool_bytes = getenv("BAMBU_EM_POOL_BYTES") ? pool : std::max<int64_t>(pool, (int64_t)s.pool.cap / 16 * 16);
     TRY(s.grp_row_ptr.ensure(8 * (size_t)(ng + 1), &s.device_bytes));
     TRY(s.grp_col_ptr.ensure(8 * (size_t)(ng + 1), &s.device_bytes));
-    TRY(s.row_nnz_ptr.ensure(8 * (size_t)(rows + 1), &s.device_bytes));
+    TRY(s.row_nnz_ptr.ensure(8 * (size_t)((s.v2 ? ng : rows) + 1), &s.device_bytes));
+    if (s.v2) TRY(s.grp_idx_off.ensure(8 * (size_t)(ng + 1), &s.device_bytes));
     TRY(s.img.ensure((size_t)off, &s.device_bytes));
     TRY(s.pool.ensure((size_t)s.pool_bytes, &s.device_bytes));
     TRY(s.img_off.ensure(8 * (size_t)(ng + 1), &s.device_bytes));
@@ -553,7 +599,12 @@ static int slot_prepare(Slot &s, const int64_t *grp_row_ptr, const int64_t *grp_
         CUDA_TRY(cudaMemcpyAsync(s.gdesc.p, s.h_gdesc.p, sizeof(GiantDesc) * giants.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(s.grp_row_ptr.p, grp_row_ptr + g0, 8 * (size_t)(ng + 1), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(s.grp_col_ptr.p, grp_col_ptr + g0, 8 * (size_t)(ng + 1), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(s.row_nnz_ptr.p, row_nnz_ptr + s.r0, 8 * (size_t)(rows + 1), cudaMemcpyHostToDevice, st));
+    if (s.v2) {
+        CUDA_TRY(cudaMemcpyAsync(s.row_nnz_ptr.p, grp_ent_ptr + g0, 8 * (size_t)(ng + 1), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(s.grp_idx_off.p, idx_off, 8 * (size_t)(ng + 1), cudaMemcpyHostToDevice, st));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(s.row_nnz_ptr.p, row_nnz_ptr + s.r0, 8 * (size_t)(rows + 1), cudaMemcpyHostToDevice, st));
+    }
     CUDA_TRY(cudaMemcpyAsync(s.img_off.p, img_off, 8 * (size_t)(ng + 1), cudaMemcpyHostToDevice, st));
     if (woff) CUDA_TRY(cudaMemcpyAsync(s.work.p, work, 4 * woff, cudaMemcpyHostToDevice, st));
     s.prepared = true;
@@ -595,11 +646,72 @@ static int slot_upload(Slot &s, const int32_t *col_idx, const double *aval, cons
     return BAMBU_EM_OK;
 }
 
+// H2D of the range's payload in the wire form v2 from the caller's HOST arrays (include/bambu_em.h)
+struct WireHost {
+    const uint32_t *row_end;
+    const double *rs, *aval;
+    const uint8_t *cidx;
+    const uint32_t *eq_bits;
+    int32_t col_mode;
+    const void *colY, *colK;
+    const uint32_t *multi_bits;
+};
+
+static int slot_upload_v2(Slot &s, const WireHost &h)
+{
+    const size_t ne = (size_t)s.nnz(), nc = (size_t)s.cols(), nr = (size_t)s.rows();
+    if ((ne && (!h.aval || !h.cidx || !h.eq_bits)) || (nc && (!h.colY || !h.colK || !h.multi_bits)) || (nr && (!h.row_end || !h.rs)))
+        return fail(BAMBU_EM_EINVAL, "NULL payload pointer");
+    if (h.col_mode != 0 && h.col_mode != 1) return fail(BAMBU_EM_EINVAL, "col_mode must be 0 (Y, K as doubles) or 1 (nobs, K as int32)");
+    const size_t cw = h.col_mode == 0 ? 8 : 4;
+    const size_t ibytes = (size_t)(s.ib1 - s.ib0);
+    const int64_t ew0 = s.e0 >> 5, ew1 = (s.e1 + 31) >> 5, cw0 = s.c0 >> 5, cw1 = (s.c1 + 31) >> 5;
+    // one allocation, 8-byte items first: aval | rs | colY | colK | row_end | eq words | multi words | index blob
+    const size_t need = 8 * ne + 8 * nr + 2 * cw * nc + 4 * nr + 4 * (size_t)(ew1 - ew0) + 4 * (size_t)(cw1 - cw0) + ibytes + 64;
+    TRY(s.payload.ensure(need, &s.device_bytes));
+    uint8_t *q = s.payload.as<uint8_t>();
+    double *d_aval = (double *)q; q += 8 * ne;
+    double *d_rs = (double *)q; q += 8 * nr;
+    uint8_t *d_cY = q; q += cw * nc;
+    uint8_t *d_cK = q; q += cw * nc;
+    uint32_t *d_re = (uint32_t *)q; q += 4 * nr;
+    uint32_t *d_eq = (uint32_t *)q; q += 4 * (size_t)(ew1 - ew0);
+    uint32_t *d_mb = (uint32_t *)q; q += 4 * (size_t)(cw1 - cw0);
+    uint8_t *d_ix = q;
+    cudaStream_t st = s.stream;
+    if (ne) {
+        CUDA_TRY(cudaMemcpyAsync(d_aval, h.aval + s.e0, 8 * ne, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_eq, h.eq_bits + ew0, 4 * (size_t)(ew1 - ew0), cudaMemcpyHostToDevice, st));
+        if (ibytes) CUDA_TRY(cudaMemcpyAsync(d_ix, h.cidx + s.ib0, ibytes, cudaMemcpyHostToDevice, st));
+    }
+    if (nr) {
+        CUDA_TRY(cudaMemcpyAsync(d_rs, h.rs + s.r0, 8 * nr, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_re, h.row_end + s.r0, 4 * nr, cudaMemcpyHostToDevice, st));
+    }
+    if (nc) {
+        CUDA_TRY(cudaMemcpyAsync(d_cY, (const uint8_t *)h.colY + cw * (size_t)s.c0, cw * nc, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_cK, (const uint8_t *)h.colK + cw * (size_t)s.c0, cw * nc, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_mb, h.multi_bits + cw0, 4 * (size_t)(cw1 - cw0), cudaMemcpyHostToDevice, st));
+    }
+    s.w_aval = d_aval - s.e0; s.w_rs = d_rs - s.r0; s.w_row_end = d_re - s.r0;
+    s.w_colY = d_cY - cw * (size_t)s.c0; s.w_colK = d_cK - cw * (size_t)s.c0;
+    s.w_eq_bits = d_eq - ew0; s.w_multi_bits = d_mb - cw0;
+    s.w_cidx = d_ix - s.ib0;
+    s.col_mode = h.col_mode;
+    s.payload_bound = false;
+    s.payload_ready = true;
+    return BAMBU_EM_OK;
+}
+
 // ---- streamed tier launches over descs [first, first + count) ---------------------------------
 static int launch_giant_pack(Slot &s, const SlotViews &v, int first, int count, cudaStream_t st)
 {
-    pack_giant_kernel<1024><<<count, 1024, 0, st>>>(v.A, s.gdesc.as<GiantDesc>() + first, count, s.gbuf.as<uint8_t>(),
-                                                     v.nnz_nonzero, &v.ctrl->err);
+    if (s.v2)
+        pack_giant_kernel<1024, true><<<count, 1024, 0, st>>>(v.A, v.W, s.gdesc.as<GiantDesc>() + first, count,
+                                                               s.gbuf.as<uint8_t>(), v.nnz_nonzero, &v.ctrl->err);
+    else
+        pack_giant_kernel<1024, false><<<count, 1024, 0, st>>>(v.A, v.W, s.gdesc.as<GiantDesc>() + first, count,
+                                                                s.gbuf.as<uint8_t>(), v.nnz_nonzero, &v.ctrl->err);
     CUDA_TRY(cudaGetLastError());
     s.launches += 1;
     return BAMBU_EM_OK;
@@ -661,8 +773,12 @@ static int slot_enqueue(Slot &s)
         CUDA_TRY(cudaStreamWaitEvent(st, s.buckets[b].done, 0));
     }
     if (s.n_single) {
-        pack_resident_kernel<64><<<s.n_single, 64, 0, st>>>(v.A, s.d_single, s.n_single, v.img_off, s.img.as<uint8_t>(),
-                                                            v.info, v.nnz_nonzero, v.est, v.status, &v.ctrl->err, 1);
+        if (s.v2)
+            pack_resident_wire_kernel<64><<<s.n_single, 64, 0, st>>>(v.W, s.d_single, s.n_single, v.img_off, s.img.as<uint8_t>(),
+                                                                     v.info, v.nnz_nonzero, v.est, v.status, &v.ctrl->err, 1);
+        else
+            pack_resident_kernel<64><<<s.n_single, 64, 0, st>>>(v.A, s.d_single, s.n_single, v.img_off, s.img.as<uint8_t>(),
+                                                                v.info, v.nnz_nonzero, v.est, v.status, &v.ctrl->err, 1);
         CUDA_TRY(cudaGetLastError());
         s.launches += 1;
     }
@@ -760,6 +876,8 @@ static int slot_finish(Slot &s)
         if (err == 0) { s.finished = true; return BAMBU_EM_OK; }
         if (err & kErrColRange) return fail(BAMBU_EM_EINVAL, "col_idx outside its group's column range");
         if (err & kErrColOrder) return fail(BAMBU_EM_EINVAL, "col_idx not strictly increasing inside a row");
+        if (err & kErrRowPtr) return fail(BAMBU_EM_EINVAL, "row_end decreases or runs past its group's entries");
+        if (err & kErrParity) return fail(BAMBU_EM_EINVAL, "a live column carries both index parities");
         if (err & kErrPool) {
             s.pool_bytes *= 2;
             TRY(s.pool.ensure((size_t)s.pool_bytes, &s.device_bytes));
@@ -814,7 +932,7 @@ int bambu_em_device_count(void)
     int ok = 0;
     for (int d = 0; d < n; ++d) {
         cudaDeviceProp prop;
-        if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) ++ok;
+        if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10 && prop.minor == 0) ++ok;
     }
     return ok;
 }
@@ -849,6 +967,21 @@ static int check_arrays(int64_t n_groups, const int64_t *grp_row_ptr, const int6
     if (!grp_row_ptr || !grp_col_ptr || !row_nnz_ptr) return fail(BAMBU_EM_EINVAL, "NULL pointer array");
     if (grp_row_ptr[0] != 0 || grp_col_ptr[0] != 0 || row_nnz_ptr[0] != 0)
         return fail(BAMBU_EM_EINVAL, "pointer arrays must start at 0");
+    // one O(G) pass before any of these is used as an index into another array
+    for (int64_t g = 0; g < n_groups; ++g)
+        if (grp_row_ptr[g + 1] < grp_row_ptr[g] || grp_col_ptr[g + 1] < grp_col_ptr[g])
+            return fail(BAMBU_EM_EINVAL, "group pointer arrays must be non-decreasing (group %lld)", (long long)g);
+    return BAMBU_EM_OK;
+}
+
+// the same for the wire form v2: all three arrays are per group
+static int check_arrays_v2(int64_t n_groups, const int64_t *grp_row_ptr, const int64_t *grp_col_ptr,
+                           const int64_t *grp_ent_ptr)
+{
+    TRY(check_arrays(n_groups, grp_row_ptr, grp_col_ptr, grp_ent_ptr));
+    for (int64_t g = 0; g < n_groups; ++g)
+        if (grp_ent_ptr[g + 1] < grp_ent_ptr[g])
+            return fail(BAMBU_EM_EINVAL, "grp_ent_ptr must be non-decreasing (group %lld)", (long long)g);
     return BAMBU_EM_OK;
 }
 
@@ -912,6 +1045,7 @@ int bambu_em_plan_upload(bambu_em_plan *p, const int32_t *col_idx, const double 
                          const double *Y, const double *K, const uint8_t *col_flags)
 {
     if (!p) return fail(BAMBU_EM_EINVAL, "plan is NULL");
+    if (p->slot.v2) return fail(BAMBU_EM_ESTATE, "the plan was created for the wire form v2 (use bambu_em_plan_upload_v2)");
     TRY(ensure_device());
     return slot_upload(p->slot, col_idx, aval, nz_flags, Y, K, col_flags);
 }
@@ -922,6 +1056,7 @@ int bambu_em_plan_bind_device(bambu_em_plan *p, const int32_t *d_col_idx, const 
 {
     if (!p) return fail(BAMBU_EM_EINVAL, "plan is NULL");
     Slot &s = p->slot;
+    if (s.v2) return fail(BAMBU_EM_ESTATE, "the plan was created for the wire form v2");
     CUDA_TRY(cudaStreamSynchronize(s.stream));
     s.v_col_idx = d_col_idx; s.v_aval = d_aval; s.v_nz_flags = d_nz_flags;
     s.v_Y = d_Y; s.v_K = d_K; s.v_col_flags = d_col_flags;
@@ -1029,6 +1164,14 @@ static int64_t chunk_target_bytes()
     return (int64_t)(mb * 1048576.0);
 }
 
+static int64_t chunk_target_bytes_v2()
+{
+    const char *e = getenv("BAMBU_EM_CHUNK_MB");
+    double mb = e ? atof(e) : 96.0;       // ~ the same number of groups per chunk as 256 MB of the v1 arena
+    if (!(mb > 0.0)) mb = 96.0;
+    return (int64_t)(mb * 1048576.0);
+}
+
 static int collect(Slot &s)   // finish a pipelined chunk: wait, (retry), download
 {
     if (!s.busy) return BAMBU_EM_OK;
@@ -1091,6 +1234,95 @@ static int batched_impl(int64_t n_groups, const int64_t *grp_row_ptr, const int6
             rc = fail(BAMBU_EM_ECUDA, "pipeline stream failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (n_groups == 0) return BAMBU_EM_OK;
     return rc;
+}
+
+// the same pipeline fed with the wire form v2
+static int batched_impl_v2(int64_t n_groups, const int64_t *grp_row_ptr, const int64_t *grp_col_ptr,
+                           const int64_t *grp_ent_ptr, const WireHost &h, int32_t maxiter, double minvalue, double conv,
+                           double *est, int32_t *iters, int32_t *status)
+{
+    if (!est || !iters || !status) return fail(BAMBU_EM_EINVAL, "NULL output pointer");
+    TRY(check_arrays_v2(n_groups, grp_row_ptr, grp_col_ptr, grp_ent_ptr));
+    TRY(ensure_device());
+    g_pipe_used = true;
+    const int64_t total_rows = grp_row_ptr[n_groups];
+    const int64_t target_max = chunk_target_bytes_v2();
+    const int64_t colb = h.col_mode == 0 ? 16 : 8;
+    int rc = BAMBU_EM_OK;
+    int64_t g0 = 0, ib0 = 0;
+    int k = 0;
+    while (g0 < n_groups && !rc) {
+        const int64_t ramp = (int64_t)12 << (20 + (k < 6 ? k : 6));       // 12 MB doubling: the wire form is ~1/3 of v1
+        const int64_t target = ramp < target_max ? ramp : target_max;
+        int64_t g1 = g0, bytes = 0;
+        while (g1 < n_groups && (g1 == g0 || bytes < target)) {
+            const int64_t rows = grp_row_ptr[g1 + 1] - grp_row_ptr[g1], cols = grp_col_ptr[g1 + 1] - grp_col_ptr[g1];
+            const int64_t e = grp_ent_ptr[g1 + 1] - grp_ent_ptr[g1];
+            bytes += (8 + wire_idx_width(cols)) * e + colb * cols + 12 * rows + 32;
+            ++g1;
+        }
+        Slot &s = g_pipe[k % 3];
+        ++k;
+        rc = collect(s);
+        if (rc) break;
+        s.single_tx_shortcut = true;
+        rc = slot_prepare(s, grp_row_ptr, grp_col_ptr, nullptr, g0, g1, grp_ent_ptr, ib0);
+        if (!rc) rc = slot_upload_v2(s, h);
+        if (!rc) rc = slot_run(s, maxiter, minvalue, conv);
+        if (!rc) {
+            s.busy = true;
+            s.dl_est = est; s.dl_iters = iters; s.dl_status = status; s.dl_total_rows = total_rows;
+            ib0 = s.ib1;
+        }
+        g0 = g1;
+    }
+    for (Slot &s : g_pipe) {
+        int rc2 = collect(s);
+        if (!rc) rc = rc2;
+    }
+    for (Slot &s : g_pipe)
+        if (s.inited && cudaStreamSynchronize(s.stream) != cudaSuccess && !rc)
+            rc = fail(BAMBU_EM_ECUDA, "pipeline stream failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (n_groups == 0) return BAMBU_EM_OK;
+    return rc;
+}
+
+int bambu_em_batched_v2(int64_t n_groups, const int64_t *grp_row_ptr, const int64_t *grp_col_ptr,
+                        const int64_t *grp_ent_ptr, const uint32_t *row_end, const double *rs, const double *aval,
+                        const void *cidx, const uint32_t *eq_bits, int32_t col_mode, const void *colY, const void *colK,
+                        const uint32_t *multi_bits, int32_t maxiter, double minvalue, double conv, double *est,
+                        int32_t *iters, int32_t *status)
+{
+    const WireHost h = {row_end, rs, aval, (const uint8_t *)cidx, eq_bits, col_mode, colY, colK, multi_bits};
+    return batched_impl_v2(n_groups, grp_row_ptr, grp_col_ptr, grp_ent_ptr, h, maxiter, minvalue, conv, est, iters, status);
+}
+
+int bambu_em_plan_create_v2(bambu_em_plan **out, int64_t n_groups, const int64_t *grp_row_ptr,
+                            const int64_t *grp_col_ptr, const int64_t *grp_ent_ptr)
+{
+    if (!out) return fail(BAMBU_EM_EINVAL, "plan pointer is NULL");
+    *out = nullptr;
+    TRY(check_arrays_v2(n_groups, grp_row_ptr, grp_col_ptr, grp_ent_ptr));
+    TRY(ensure_device());
+    bambu_em_plan *p = new (std::nothrow) bambu_em_plan;
+    if (!p) return fail(BAMBU_EM_ENOMEM, "out of host memory");
+    p->n_groups = n_groups;
+    int rc = slot_prepare(p->slot, grp_row_ptr, grp_col_ptr, nullptr, 0, n_groups, grp_ent_ptr, 0);
+    if (!rc && cudaStreamSynchronize(p->slot.stream) != cudaSuccess) rc = fail(BAMBU_EM_ECUDA, "structure upload failed");
+    if (rc) { bambu_em_plan_destroy(p); return rc; }
+    *out = p;
+    return BAMBU_EM_OK;
+}
+
+int bambu_em_plan_upload_v2(bambu_em_plan *p, const uint32_t *row_end, const double *rs, const double *aval,
+                            const void *cidx, const uint32_t *eq_bits, int32_t col_mode, const void *colY,
+                            const void *colK, const uint32_t *multi_bits)
+{
+    if (!p) return fail(BAMBU_EM_EINVAL, "plan is NULL");
+    if (!p->slot.v2) return fail(BAMBU_EM_ESTATE, "the plan was created for the v1 arena");
+    TRY(ensure_device());
+    const WireHost h = {row_end, rs, aval, (const uint8_t *)cidx, eq_bits, col_mode, colY, colK, multi_bits};
+    return slot_upload_v2(p->slot, h);
 }
 
 int bambu_em_batched(int64_t n_groups, const int64_t *grp_row_ptr, const int64_t *grp_col_ptr,

@@ -20,6 +20,45 @@ struct ArenaDev {
     int64_t n_groups, total_rows;
 };
 
+// ---- wire form v2 ("live arena"), device pointers (include/bambu_em.h, bambu_em_batched_v2) -----------
+// What the packer can drop without changing a result bit is dropped before the copy: columns with
+// Y == 0, entries with aval == 0 (see the image comment below); rs_i -- which sums ALL entries of a
+// row (src/em.cpp:33) -- therefore travels as a per-row value.  Entries carry the LIVE column index
+// and the parity of the ORIGINAL column index (bit 0), which is all the summation order needs.
+struct WireDev {
+    const int64_t *grp_row_ptr, *grp_col_ptr, *grp_ent_ptr;   // rows / live columns / live entries per group
+    const int64_t *grp_idx_off;     // byte offset of the group's index block inside cidx (library-computed)
+    const uint32_t *row_end;        // per row: end of its entries, relative to the group's first entry
+    const double *rs;               // per row
+    const double *aval;             // per entry
+    const uint8_t *cidx;            // per group u16[e] (NL <= 32767) or u32[e]: live_col << 1 | parity
+    const uint32_t *eq_bits;        // bit k: entry k is `equal`
+    const void *colY, *colK;        // col_mode 0: f64 Y, f64 K; 1: i32 nobs, i32 K (Y = nobs / K)
+    const uint32_t *multi_bits;     // bit j: live column j is multi_align
+    int32_t col_mode;
+    int64_t n_groups, total_rows;
+};
+
+__host__ __device__ inline int wire_idx_width(int64_t NL) { return NL <= 32767 ? 2 : 4; }
+
+__device__ __forceinline__ uint32_t wire_bit(const uint32_t *bits, int64_t k)
+{
+    return (bits[k >> 5] >> (uint32_t)(k & 31)) & 1u;
+}
+
+// Y_j and K_j of live column j (absolute index).  Mode 1 forms Y = nobs / K on the device exactly as
+// R does on the host (R/bambu-quantify_utilityFunctions.R:221-228: n.obs = nobs / K, both integer-valued).
+__device__ __forceinline__ void wire_col(const WireDev &W, int64_t j, double &y, double &k)
+{
+    if (W.col_mode == 0) {
+        y = static_cast<const double *>(W.colY)[j];
+        k = static_cast<const double *>(W.colK)[j];
+    } else {
+        k = (double)static_cast<const int32_t *>(W.colK)[j];
+        y = __ddiv_rn((double)static_cast<const int32_t *>(W.colY)[j], k);
+    }
+}
+
 // ---- what the pack kernel found in a group ------------------------------------
 struct PackInfo {
     int32_t NL;     // live columns: Y != 0
@@ -165,6 +204,8 @@ constexpr int kErrColOrder = 2;   // col_idx not strictly increasing inside a ro
 constexpr int kErrPool = 4;       // image pool exhausted (the host grows it and reruns)
 constexpr int kErrTooBig = 8;     // a group's SELL image exceeds shared memory (the host moves the group
                                   // to the streamed tier)
+constexpr int kErrRowPtr = 16;    // wire v2: row_end decreasing or beyond the group's entries
+constexpr int kErrParity = 32;    // wire v2: one live column carries both parities
 
 // ---- block-wide exclusive scan, in place, n arbitrary ---------------------------
 template <int T>

@@ -79,9 +79,9 @@ __host__ inline void giant_layout(GiantDesc &d, int64_t M, int64_t N, int64_t e)
 }
 
 // ---- pack ------------------------------------------------------------------------------
-template <int T>
+template <int T, bool V2>
 __global__ void __launch_bounds__(T)
-pack_giant_kernel(ArenaDev A, GiantDesc *__restrict__ descs, int n_giant, uint8_t *__restrict__ gbuf,
+pack_giant_kernel(ArenaDev A, WireDev W, GiantDesc *__restrict__ descs, int n_giant, uint8_t *__restrict__ gbuf,
                   int64_t *__restrict__ nnz_nonzero, int *__restrict__ err_flag)
 {
     __shared__ uint32_t s_warp[34];
@@ -90,8 +90,6 @@ pack_giant_kernel(ArenaDev A, GiantDesc *__restrict__ descs, int n_giant, uint8_
     GiantDesc &D = descs[blockIdx.x];
     const int tid = threadIdx.x;
     const int g = D.g, M = D.M, N = D.N;
-    const int64_t row0 = A.grp_row_ptr[g], col0 = A.grp_col_ptr[g];
-    const int64_t *rnp = A.row_nnz_ptr + row0;
     uint8_t *img = gbuf + D.base;
     double *rs = reinterpret_cast<double *>(img + D.rs);
     double *Yl = reinterpret_cast<double *>(img + D.Yl);
@@ -110,10 +108,81 @@ pack_giant_kernel(ArenaDev A, GiantDesc *__restrict__ descs, int n_giant, uint8_
     uint32_t *hcnt = reinterpret_cast<uint32_t *>(img + D.hcnt);
 
     if (tid == 0) s_nz = 0;
+    uint32_t NL, nnzL;
+    if (V2) {
+        // wire form v2: the columns are the live ones, the rows are compacted, rs is given (common.cuh: WireDev)
+        const int64_t row0 = W.grp_row_ptr[g], col0 = W.grp_col_ptr[g], ent0 = W.grp_ent_ptr[g];
+        const uint32_t *rend = W.row_end + row0;
+        const uint16_t *cidx16 = reinterpret_cast<const uint16_t *>(W.cidx + W.grp_idx_off[g]);
+        const uint32_t *cidx32 = reinterpret_cast<const uint32_t *>(W.cidx + W.grp_idx_off[g]);
+        const bool wide = wire_idx_width(N) == 4;
+        const double *av = W.aval + ent0;
+        NL = (uint32_t)N;
+        nnzL = (uint32_t)(W.grp_ent_ptr[g + 1] - ent0);
+        for (int j = tid; j < N; j += T) {
+            double y, kk;
+            wire_col(W, col0 + j, y, kk);
+            Yl[j] = y;
+            KY[j] = __dmul_rn(kk, y);
+            cm[j] = (uint8_t)wire_bit(W.multi_bits, col0 + j);
+            colmap[j] = 0;          // parities seen
+        }
+        for (int j = tid; j <= N; j += T) colcnt[j] = 0;
+        __syncthreads();
+        if (tid == 0) {
+            cm[NL] = 0;
+            if (M > 0 && rend[M - 1] != nnzL) atomicOr(err_flag, kErrRowPtr);
+        }
+        for (int i = tid; i < M; i += T) {
+            const uint32_t lo = i ? rend[i - 1] : 0u, hi = rend[i];
+            uint32_t ne = 0, no = 0;
+            if (hi < lo || hi > nnzL) atomicOr(err_flag, kErrRowPtr);
+            else {
+                int prev = -1;
+                for (uint32_t k = lo; k < hi; ++k) {
+                    const uint32_t c = wide ? cidx32[k] : (uint32_t)cidx16[k];
+                    const uint32_t lj = c >> 1;
+                    if (lj >= NL) { atomicOr(err_flag, kErrColRange); continue; }
+                    if ((int)lj <= prev) atomicOr(err_flag, kErrColOrder);
+                    prev = (int)lj;
+                    if (c & 1u) ++no; else ++ne;
+                }
+            }
+            rs[i] = W.rs[row0 + i];
+            hcnt[2 * i] = ne;
+            hcnt[2 * i + 1] = no;
+        }
+        __syncthreads();
+        const uint32_t kept = block_excl_scan<T>(hcnt, 2 * M, s_warp);
+        for (int t = tid; t < 2 * M; t += T) hp[t] = hcnt[t];
+        if (tid == 0) { hp[2 * M] = kept; s_nz = nnzL; }
+        __syncthreads();
+        nnzL = kept;            // == the group's entry count unless an index was out of range (then an error is set)
+        for (int i = tid; i < M; i += T) {
+            const uint32_t lo = i ? rend[i - 1] : 0u, hi = rend[i];
+            if (hi < lo || hi > (uint32_t)(W.grp_ent_ptr[g + 1] - ent0)) continue;
+            uint32_t pe = hcnt[2 * i], po = hcnt[2 * i + 1];
+            for (uint32_t k = lo; k < hi; ++k) {
+                const uint32_t c = wide ? cidx32[k] : (uint32_t)cidx16[k];
+                const uint32_t lj = c >> 1;
+                if (lj >= NL) continue;
+                const uint32_t pos = (c & 1u) ? po++ : pe++;
+                cidx[pos] = lj;
+                cval[pos] = av[k];
+                eq[pos] = (uint8_t)wire_bit(W.eq_bits, ent0 + k);
+                atomicAdd(&colcnt[lj], 1u);
+                atomicOr(&colmap[lj], 1u << (c & 1u));
+            }
+        }
+        __syncthreads();
+        for (int j = tid; j < N; j += T) if (colmap[j] == 3u) atomicOr(err_flag, kErrParity);
+    } else {
+    const int64_t row0 = A.grp_row_ptr[g], col0 = A.grp_col_ptr[g];
+    const int64_t *rnp = A.row_nnz_ptr + row0;
     // A: live columns
     for (int j = tid; j < N; j += T) colmap[j] = (A.Y[col0 + j] != 0.0) ? 1u : 0u;
     __syncthreads();
-    const uint32_t NL = block_excl_scan<T>(colmap, N, s_warp);
+    NL = block_excl_scan<T>(colmap, N, s_warp);
     for (int j = tid; j < N; j += T) {
         const bool live = (A.Y[col0 + j] != 0.0);
         const uint32_t lj = colmap[j];
@@ -151,7 +220,7 @@ pack_giant_kernel(ArenaDev A, GiantDesc *__restrict__ descs, int n_giant, uint8_
     }
     if (my_nz) atomicAdd(&s_nz, my_nz);
     __syncthreads();
-    const uint32_t nnzL = block_excl_scan<T>(hcnt, 2 * M, s_warp);
+    nnzL = block_excl_scan<T>(hcnt, 2 * M, s_warp);
     for (int t = tid; t < 2 * M; t += T) hp[t] = hcnt[t];
     if (tid == 0) hp[2 * M] = nnzL;
     __syncthreads();
@@ -172,6 +241,7 @@ pack_giant_kernel(ArenaDev A, GiantDesc *__restrict__ descs, int n_giant, uint8_
                 atomicAdd(&colcnt[lj], 1u);
             }
         }
+    }
     }
     __syncthreads();
     block_excl_scan<T>(colcnt, (int)NL, s_warp);

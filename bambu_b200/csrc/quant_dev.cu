@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <atomic>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <type_traits>
 #include <vector>
@@ -212,14 +213,19 @@ struct Uploader {
                 issued[c].store(1, std::memory_order_release);
                 continue;
             }
-            th[c] = std::thread([this, c] {
+            auto copy_column = [this, c] {
                 cudaError_t e = cudaSetDevice(device);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(cols[c].dst, cols[c].src, cols[c].bytes, cudaMemcpyHostToDevice, st[c]);
                 if (e == cudaSuccess) e = cudaEventRecord(ev[c], st[c]);
                 if (e != cudaSuccess) error.store((int)e);
                 done_ms[c] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
                 issued[c].store(1, std::memory_order_release);
-            });
+            };
+            try {
+                th[c] = std::thread(copy_column);
+            } catch (const std::system_error &) {     // no thread to be had: copy this column from the calling thread
+                copy_column();
+            }
         }
     }
     void finish()
@@ -586,6 +592,12 @@ int quantdt_core(int64_t n, const IdT *gene_code, const IdT *txid, const IdT *eq
     } catch (const std::bad_alloc &) {
         bambu_quant_set_error("out of memory in the device packer");
         return BAMBU_EM_ENOMEM;
+    } catch (const std::exception &e) {       // nothing may unwind through the C ABI (thread creation, std::function, ...)
+        bambu_quant_set_error(std::string("device packer: ") + e.what());
+        return BAMBU_EM_ECUDA;
+    } catch (...) {
+        bambu_quant_set_error("device packer: unknown exception");
+        return BAMBU_EM_ECUDA;
     }
 }
 
@@ -641,6 +653,14 @@ int bambu_quant_pack_create_gpu(bambu_quant_pack **out, int64_t n, const int64_t
         bambu_quant_set_error("out of memory in the device packer");
         delete P;
         return BAMBU_EM_ENOMEM;
+    } catch (const std::exception &e) {
+        bambu_quant_set_error(std::string("device packer: ") + e.what());
+        delete P;
+        return BAMBU_EM_ECUDA;
+    } catch (...) {
+        bambu_quant_set_error("device packer: unknown exception");
+        delete P;
+        return BAMBU_EM_ECUDA;
     }
     if (used_device) *used_device = 1;
     *out = P;

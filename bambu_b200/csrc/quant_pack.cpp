@@ -155,6 +155,9 @@ int bambu_quant_pack_create(bambu_quant_pack **out, int64_t n, const int64_t *ge
         g_pack_error = "Columns GENEID, txid, eqClassId, nobs, are missing from object.";   // R/...utilityFunctions.R:199-203
         return BAMBU_EM_EINVAL;
     }
+    // the arena carries txid as int32 (R's integer): anything wider would be truncated and merged under a wrong id
+    for (int64_t i = 0; i < n; ++i)
+        if (txid_in[i] < INT32_MIN || txid_in[i] > INT32_MAX) { g_pack_error = "txid outside the 32-bit integer range"; return BAMBU_EM_EINVAL; }
     bambu_quant_pack *P = new (std::nothrow) bambu_quant_pack;
     if (!P) { g_pack_error = "out of memory"; return BAMBU_EM_ENOMEM; }
     const size_t N = (size_t)n;
@@ -401,6 +404,14 @@ int bambu_quant_pack_create(bambu_quant_pack **out, int64_t n, const int64_t *ge
         g_pack_error = "out of memory";
         delete P;
         return BAMBU_EM_ENOMEM;
+    } catch (const std::exception &e) {
+        g_pack_error = e.what();
+        delete P;
+        return BAMBU_EM_EINVAL;
+    } catch (...) {
+        g_pack_error = "unknown exception in the host packer";
+        delete P;
+        return BAMBU_EM_EINVAL;
     }
     *out = P;
     return BAMBU_EM_OK;

@@ -37,9 +37,86 @@ def shard_groups(arena, world, expected_iters=None):
     """One sample's gene groups -> ranks by LPT on nnz x expected iterations
     (giant loci first).  Returns, per rank, the group ids in arena order."""
     _, _, e = arena.group_shapes()
-    w = e.astype(np.float64) * (1.0 if expected_iters is None else np.asarray(expected_iters, dtype=np.float64))
+    return shard_groups_by_weight(e, world, expected_iters)
+
+
+def shard_groups_by_weight(entries, world, expected_iters=None):
+    """The same from per-group entry counts alone (e.g. the a-priori sizes of an annotation, before any rank has
+    built its part of the arena): LPT places the heaviest groups -- the giant loci -- first."""
+    w = np.asarray(entries, dtype=np.float64) * (1.0 if expected_iters is None else np.asarray(expected_iters, dtype=np.float64))
     part = lpt_partition(w, world)
     return [np.nonzero(part == r)[0] for r in range(world)]
+
+
+class SharedHostTable:
+    """The combined estimate table of a one-box run, gathered on the HOST side: one POSIX shared-memory segment
+    that every rank maps (and page-locks when CUDA is there).  A rank's C-ABI call downloads its ``est[3, rows_r]``
+    straight into its slice over its own PCIe link; ``gather()`` is then only a barrier, after which rank 0 holds
+    every rank's table (``tables()``) -- the reference's ``combineCountSes`` cbind (R/bambu_utilityFunctions.R:215-241)
+    without a second pass over any link.  ``EstimateGatherer`` is the NCCL alternative (tables travel GPU -> GPU 0 ->
+    host over rank 0's link)."""
+
+    def __init__(self, rows_local: int, group=None, pin: bool = True):
+        import torch
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+        self.dist, self.group = dist, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        allr = [None] * self.world
+        dist.all_gather_object(allr, int(rows_local), group=group)
+        self.rows = [int(x) for x in allr]
+        off = np.concatenate(([0], np.cumsum([3 * 8 * r for r in self.rows]))).astype(np.int64)
+        self.total = int(max(off[-1], 8))
+        name = [None]
+        if self.rank == 0:
+            try:
+                import os
+                st = os.statvfs("/dev/shm")
+                if st.f_bavail * st.f_frsize < self.total + (64 << 20):
+                    raise OSError("not enough room in /dev/shm")
+                self.shm = shared_memory.SharedMemory(create=True, size=self.total)
+                name[0] = self.shm.name
+            except OSError:
+                name[0] = None
+        dist.broadcast_object_list(name, src=0, group=group)
+        if name[0] is None:        # every rank raises: the caller falls back to the NCCL gather
+            raise RuntimeError("SharedHostTable: no shared memory for %d bytes" % self.total)
+        if self.rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+        buf = np.frombuffer(self.shm.buf, dtype=np.uint8, count=self.total)
+        self._views = [buf[off[r]:off[r + 1]].view(np.float64).reshape(3, self.rows[r]) for r in range(self.world)]
+        self.mine = self._views[self.rank]
+        self.mine[...] = 0.0                      # touch the pages from the rank that writes them
+        self.pinned = False
+        if pin and torch.cuda.is_available():
+            rc = torch.cuda.cudart().cudaHostRegister(buf.ctypes.data, self.total, 0)
+            self.pinned = int(rc) == 0
+        self._buf = buf
+        dist.barrier(group=group)
+
+    def gather(self):
+        """Every rank has finished writing its slice when this returns."""
+        self.dist.barrier(group=self.group)
+        return self.tables()
+
+    def tables(self):
+        return self._views if self.rank == 0 else None
+
+    def close(self):
+        import torch
+        try:
+            if self.pinned:
+                torch.cuda.cudart().cudaHostUnregister(self._buf.ctypes.data)
+        except Exception:
+            pass
+        self.dist.barrier(group=self.group)
+        self._views = self.mine = self._buf = None
+        try:
+            self.shm.close()
+            if self.rank == 0:
+                self.shm.unlink()
+        except Exception:
+            pass
 
 
 def gather_estimates(est, device=None, dst=0, group=None):

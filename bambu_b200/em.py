@@ -65,6 +65,38 @@ def abundance_quantification_into(arena: Arena, est, iters, status, maxiter=2000
                                   _ptr(iters), _ptr(status)))
 
 
+def _wire_args(w):
+    mode = int(w.col_mode)
+    cdt = np.int32 if mode == 1 else np.float64
+    bufs = (_c(w.row_end, np.uint32), _c(w.rs, np.float64), _c(w.aval, np.float64), _c(w.cidx, np.uint8),
+            _c(w.eq_bits, np.uint32), _c(w.colY, cdt), _c(w.colK, cdt), _c(w.multi_bits, np.uint32))
+    return bufs, mode
+
+
+def abundance_quantification_wire(wire, maxiter: int = 20000, conv: float = 1e-2, minvalue: float = 1e-8, out=None):
+    """``abundance_quantification`` fed with the wire form v2 (``bambu_b200.wire.Wire``): the same estimates,
+    iteration counts and status words from about a third of the host->device bytes (``bambu_em_batched_v2``).
+    ``out`` = optional ``(est, iters, status)`` HOST buffers (e.g. pinned)."""
+    L = _lib.lib()
+    g, c, e = _c(wire.grp_row_ptr, np.int64), _c(wire.grp_col_ptr, np.int64), _c(wire.grp_ent_ptr, np.int64)
+    (re, rs, av, ci, eq, cy, ck, mb), mode = _wire_args(wire)
+    n_groups, rows = len(g) - 1, int(g[-1])
+    if out is None:
+        est = np.zeros((3, rows), dtype=np.float64)
+        iters = np.zeros(max(n_groups, 1), dtype=np.int32)
+        status = np.zeros(max(n_groups, 1), dtype=np.int32)
+    else:
+        est, iters, status = out
+        if est.dtype != np.float64 or est.size < 3 * rows or not est.flags.c_contiguous:
+            raise ValueError("est must be a contiguous float64 buffer of 3 x rows")
+        if iters.dtype != np.int32 or status.dtype != np.int32 or iters.size < n_groups or status.size < n_groups:
+            raise ValueError("iters/status must be int32 buffers of n_groups")
+    _lib.check(L.bambu_em_batched_v2(n_groups, _ptr(g), _ptr(c), _ptr(e), _ptr(re), _ptr(rs), _ptr(av), _ptr(ci),
+                                     _ptr(eq), mode, _ptr(cy), _ptr(ck), _ptr(mb), int(maxiter), float(minvalue),
+                                     float(conv), _ptr(est), _ptr(iters), _ptr(status)))
+    return est, iters[:n_groups], status[:n_groups]
+
+
 def emWithL1(A, A_full, A_unique, Y, K, maxiter: int = 10000, minvalue: float = 1e-8, conv: float = 1e-2):
     """One dense group, the signature of the reference's ``emWithL1``
     (R/RcppExports.R:12).  Returns ``{"theta": 3 x M}`` like the reference
@@ -89,16 +121,18 @@ def emWithL1(A, A_full, A_unique, Y, K, maxiter: int = 10000, minvalue: float = 
 class EmPlan:
     """Arena resident in HBM (``bambu_em_plan_*``)."""
 
-    def __init__(self, arena: Arena):
+    def __init__(self, arena):
+        """``arena``: an ``Arena`` (v1) or a ``bambu_b200.wire.Wire`` (v2, ``bambu_em_plan_create_v2``)."""
         self._L = _lib.lib()
         self.arena = arena
+        self.is_wire = hasattr(arena, "grp_ent_ptr")
         self._g = _c(arena.grp_row_ptr, np.int64)
         self._c = _c(arena.grp_col_ptr, np.int64)
-        self._r = _c(arena.row_nnz_ptr, np.int64)
+        self._r = _c(arena.grp_ent_ptr if self.is_wire else arena.row_nnz_ptr, np.int64)
         self.n_groups, self.rows = len(self._g) - 1, int(self._g[-1])
         self._h = ctypes.c_void_p()
-        _lib.check(self._L.bambu_em_plan_create(ctypes.byref(self._h), self.n_groups, _ptr(self._g), _ptr(self._c),
-                                                _ptr(self._r)))
+        create = self._L.bambu_em_plan_create_v2 if self.is_wire else self._L.bambu_em_plan_create
+        _lib.check(create(ctypes.byref(self._h), self.n_groups, _ptr(self._g), _ptr(self._c), _ptr(self._r)))
         self._keep = None
 
     def reset(self, arena: Arena):
@@ -119,6 +153,13 @@ class EmPlan:
         """H2D of the payload (defaults: the arena's arrays).  The arrays are
         kept referenced until the next upload (the copy is asynchronous)."""
         a = self.arena
+        if self.is_wire:
+            bufs, mode = _wire_args(a)
+            self._keep = bufs
+            re, rs, av, ci, eq, cy, ck, mb = bufs
+            _lib.check(self._L.bambu_em_plan_upload_v2(self._h, _ptr(re), _ptr(rs), _ptr(av), _ptr(ci), _ptr(eq), mode,
+                                                       _ptr(cy), _ptr(ck), _ptr(mb)))
+            return
         bufs = (_c(a.col_idx if col_idx is None else col_idx, np.int32),
                 _c(a.aval if aval is None else aval, np.float64),
                 _c(a.nz_flags if nz_flags is None else nz_flags, np.uint8),
@@ -131,6 +172,13 @@ class EmPlan:
         """H2D from raw host addresses (e.g. pinned torch tensors)."""
         _lib.check(self._L.bambu_em_plan_upload(self._h, *[ctypes.c_void_p(int(x)) for x in
                                                            (col_idx, aval, nz_flags, Y, K, col_flags)]))
+
+    def upload_ptrs_v2(self, row_end, rs, aval, cidx, eq_bits, col_mode, colY, colK, multi_bits):
+        """H2D of a wire-form payload from raw host addresses (e.g. pinned torch tensors)."""
+        v = ctypes.c_void_p
+        _lib.check(self._L.bambu_em_plan_upload_v2(self._h, v(int(row_end)), v(int(rs)), v(int(aval)), v(int(cidx)),
+                                                   v(int(eq_bits)), int(col_mode), v(int(colY)), v(int(colK)),
+                                                   v(int(multi_bits))))
 
     def bind_device(self, col_idx, aval, nz_flags, Y, K, col_flags):
         """Use device buffers (raw device addresses) owned by the caller."""

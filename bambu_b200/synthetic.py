@@ -309,3 +309,65 @@ def cohort_sample(ann: Annotation, s: int) -> Arena:
     """Sample ``s`` of a cohort (configs 4/5): fresh counts, 20 % of the free
     classes re-drawn, per-sample d_rate ~ U(0.02, 0.3)."""
     return sample_arena(ann, s, d_rate=None, resample_frac=0.2)
+
+
+# -------------------------------------------------------------------------- config 3, locus by locus
+# ``sample_arena`` on the whole config-3 annotation sorts 1.5e8 entries at once (minutes, 20 GB).  A giant locus
+# is its own gene group (tr_dimension >= 2e8 >> 1000), so the same workload can be drawn one locus at a time --
+# every locus from its own seed -- which is also what lets a rank generate ONLY the loci of its shard.
+@dataclass
+class Config3Plan:
+    small: Annotation          # the ordinary genes (their groups come first, as assignGroups orders them)
+    giant_m: np.ndarray        # transcripts / read classes of every giant locus, in group order
+    giant_n: np.ndarray
+    seed: int
+
+    @property
+    def n_giant(self):
+        return len(self.giant_m)
+
+    def giant_expected_entries(self):
+        """a-priori entry count of a locus: one unique class per transcript + k ~ 1 + Binomial(m-1, 19/m) per free class"""
+        return self.giant_m + (self.giant_n - self.giant_m) * (1.0 + 19.0 * (self.giant_m - 1) / self.giant_m)
+
+
+def config3_plan(scale: float = 1.0, seed: int = 20260003) -> Config3Plan:
+    ng = max(1, int(round(50 * scale)))
+    Gs = max(1, int(round(5_000 * scale))) - ng
+    small = make_annotation(Gs, int(round(Gs * 250 / 60)), int(round(Gs * 500 / 60)), int(round(Gs * 2000 / 60)), seed)
+    rng = np.random.default_rng(seed + 31)
+    gm = rng.integers(2000, 4001, ng)
+    gn = rng.integers(100_000, 200_001, ng)
+    o = np.argsort(gm * gn, kind="stable")          # assignGroups: ascending tr_dimension
+    return Config3Plan(small, gm[o].astype(np.int64), gn[o].astype(np.int64), seed)
+
+
+def config3_locus(plan: Config3Plan, k: int, sample: int = 0) -> Arena:
+    """Giant locus ``k`` of the plan as a one-group arena (drawn by ``sample_arena`` from the locus' own seed)."""
+    ann = Annotation(m=plan.giant_m[k:k + 1].copy(), n=plan.giant_n[k:k + 1].copy(), lam=0.0, grp=np.ones(1, np.int64),
+                     seed=plan.seed + 1009 * (k + 1), giant=np.ones(1, bool))
+    return sample_arena(ann, sample)
+
+
+def _config3_locus_job(args):
+    scale, seed, k, sample = args
+    a = config3_locus(config3_plan(scale, seed), k, sample)
+    return (a.grp_row_ptr, a.grp_col_ptr, a.row_nnz_ptr, a.col_idx, a.aval, a.nz_flags, a.Y, a.K, a.col_flags, a.txid)
+
+
+def config3_arena(scale: float = 1.0, seed: int = 20260003, loci=None, small: bool = True, workers: int = 1,
+                  sample: int = 0, mp_context: str = "fork") -> Arena:
+    """Config 3 (BASELINE.json configs[2]): the ordinary genes' groups followed by the giant loci ``loci`` (default:
+    all), each its own group.  ``workers`` > 1 draws the loci in a process pool (``mp_context``: use "forkserver"
+    from a process that already holds a CUDA context)."""
+    plan = config3_plan(scale, seed)
+    loci = list(range(plan.n_giant)) if loci is None else [int(k) for k in loci]
+    jobs = [(scale, seed, k, sample) for k in loci]
+    if workers > 1 and len(jobs) > 1:
+        import multiprocessing as mp
+        with mp.get_context(mp_context).Pool(min(workers, len(jobs))) as pool:
+            parts = [Arena(*p) for p in pool.map(_config3_locus_job, jobs, chunksize=1)]
+    else:
+        parts = [Arena(*_config3_locus_job(j)) for j in jobs]
+    head = [sample_arena(plan.small, sample)] if small else []
+    return Arena.concatenate(head + parts)

@@ -26,7 +26,12 @@
  *   - there is NO CPU fallback: without a usable sm_100 device the calls fail
  *     with BAMBU_EM_ENODEVICE;
  *   - one host thread per process may drive a plan at a time (R is single
- *     threaded; BiocParallel workers are processes, R/bambu_utilityFunctions.R:6-15).
+ *     threaded; BiocParallel workers are processes, R/bambu_utilityFunctions.R:6-15);
+ *     the one-shot entry points (bambu_em_batched*, bambu_emWithL1, bambu_quantDT*) share a
+ *     cached device workspace and are NOT reentrant: call them from one thread at a time;
+ *   - txid values must fit R's integer (int32): the arena carries them so; wider ids are
+ *     rejected with BAMBU_EM_EINVAL;
+ *   - row_nnz_ptr has grp_row_ptr[n_groups] + 1 elements.
  *
  * Arena (segmented CSR; see bambu_b200/arena.py for the prose version)
  *   group g owns rows    [grp_row_ptr[g], grp_row_ptr[g+1])   (transcripts, txid ascending)
@@ -92,6 +97,53 @@ int bambu_em_batched(int64_t n_groups,
                      int32_t maxiter, double minvalue, double conv,
                      double *est, int32_t *iters, int32_t *status);
 
+/* ---- the same call fed with the wire form v2 ("live arena") ----------------------------------------
+ * What bounds a cohort end to end is the host->device copy of the arena, so v2 carries only what the EM
+ * reads (about 37 % of the v1 bytes on the synthetic cohorts).  The packer applies the two exact
+ * eliminations the device applies to a v1 arena -- columns with Y == 0 and entries with aval == 0 cannot
+ * change a result bit (src/em.cpp:48-49, 98-99) -- and therefore also evaluates the one quantity the dropped
+ * entries still feed, rs_i = sum_j X_ij (src/em.cpp:33; two accumulators by column parity, added at the end).
+ *
+ *   grp_row_ptr[n_groups+1]  rows of group g (as in v1)
+ *   grp_col_ptr[n_groups+1]  LIVE columns of group g (Y != 0), in the v1 column order
+ *   grp_ent_ptr[n_groups+1]  LIVE entries of group g (aval != 0 in a live column), row by row
+ *   row_end[rows]            end of the row's entries relative to its group's first entry (u32)
+ *   rs[rows]                 sum of ALL aval of the row (f64)
+ *   aval[entries]            f64
+ *   cidx                     byte blob; group g's block starts at the next multiple of 4 after group g-1's
+ *                            and holds, per entry, (live column index << 1) | (ORIGINAL column index & 1):
+ *                            uint16 while the group has at most 32767 live columns, uint32 otherwise;
+ *                            strictly increasing inside a row
+ *   eq_bits                  bit k (word k/32, bit k%32): entry k is `equal`
+ *   col_mode 1               colY = int32 nobs, colK = int32 K per live column; the device forms
+ *                            Y = nobs / K exactly as R does (R/bambu-quantify_utilityFunctions.R:221-228)
+ *   col_mode 0               colY = f64 Y, colK = f64 K per live column
+ *   multi_bits               bit j: live column j is multi_align
+ *
+ * Outputs as in bambu_em_batched.  K must be finite.  The v1 entry point stays; both give identical doubles. */
+int bambu_em_batched_v2(int64_t n_groups, const int64_t *grp_row_ptr, const int64_t *grp_col_ptr,
+                        const int64_t *grp_ent_ptr, const uint32_t *row_end, const double *rs, const double *aval,
+                        const void *cidx, const uint32_t *eq_bits, int32_t col_mode, const void *colY,
+                        const void *colK, const uint32_t *multi_bits,
+                        int32_t maxiter, double minvalue, double conv,
+                        double *est, int32_t *iters, int32_t *status);
+
+/* v1 arena -> wire form v2 (native host code, csrc/wire.cpp).  Borrowed pointers, valid until bambu_wire_free.
+ * nnz_nonzero[n_groups] = entries with aval != 0 per group incl. those of dropped columns (the nnz_g of the
+ * nnz-iterations metric).  total_bytes = what bambu_em_batched_v2 copies to the device. */
+typedef struct bambu_wire bambu_wire;
+const char *bambu_wire_last_error(void);
+int bambu_wire_create(bambu_wire **wire, int64_t n_groups, const int64_t *grp_row_ptr, const int64_t *grp_col_ptr,
+                      const int64_t *row_nnz_ptr, const int32_t *col_idx, const double *aval, const uint8_t *nz_flags,
+                      const double *Y, const double *K, const uint8_t *col_flags);
+int bambu_wire_free(bambu_wire *wire);
+int bambu_wire_sizes(const bambu_wire *wire, int64_t *n_groups, int64_t *n_rows, int64_t *n_cols, int64_t *n_entries,
+                     int64_t *cidx_bytes, int32_t *col_mode, int64_t *total_bytes);
+int bambu_wire_arrays(const bambu_wire *wire, const int64_t **grp_row_ptr, const int64_t **grp_col_ptr,
+                      const int64_t **grp_ent_ptr, const uint32_t **row_end, const double **rs, const double **aval,
+                      const void **cidx, const uint32_t **eq_bits, const void **colY, const void **colK,
+                      const uint32_t **multi_bits, const int64_t **nnz_nonzero);
+
 /* ---- one dense group: the drop-in for one emWithL1 call ------------------------
  * Replaces .Call("_bambu_emWithL1", ...) (R/RcppExports.R:13, src/em.cpp:77-110).
  * A, A_full, A_unique: M x N column-major (R matrices); Y, K: N.  est: 3 x M
@@ -129,6 +181,13 @@ int bambu_em_plan_upload(bambu_em_plan *plan, const int32_t *col_idx, const doub
 int bambu_em_plan_bind_device(bambu_em_plan *plan, const int32_t *d_col_idx, const double *d_aval,
                               const uint8_t *d_nz_flags, const double *d_Y, const double *d_K,
                               const uint8_t *d_col_flags);
+/* the plan API on the wire form v2: structure and payload as bambu_em_batched_v2 takes them.  For such a plan
+ * nnz_nonzero (bambu_em_plan_download) counts the live entries. */
+int bambu_em_plan_create_v2(bambu_em_plan **plan, int64_t n_groups, const int64_t *grp_row_ptr,
+                            const int64_t *grp_col_ptr, const int64_t *grp_ent_ptr);
+int bambu_em_plan_upload_v2(bambu_em_plan *plan, const uint32_t *row_end, const double *rs, const double *aval,
+                            const void *cidx, const uint32_t *eq_bits, int32_t col_mode, const void *colY,
+                            const void *colK, const uint32_t *multi_bits);
 /* enqueue pack + EM kernels (asynchronous) */
 int bambu_em_plan_run(bambu_em_plan *plan, int32_t maxiter, double minvalue, double conv);
 /* asynchronous D2H of the outputs into HOST buffers, then wait for completion.

@@ -42,6 +42,16 @@ def _worker(rank, world, port, q):
     got = bdist.gather_estimates(est)
     g2 = bdist.EstimateGatherer(est.shape[1], "cpu")
     got2 = g2(np.ascontiguousarray(est))
+    # host-side gather: every rank writes its slice of one shared-memory table, rank 0 reads all of them
+    tab = bdist.SharedHostTable(est.shape[1])
+    tab.mine[...] = est
+    got3 = tab.gather()
+    if rank == 0:
+        assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(got, got3))
+    else:
+        assert got3 is None
+    got3 = None
+    tab.close()
     if rank == 0:
         assert all(np.array_equal(a, b.numpy(), equal_nan=True) for a, b in zip(got, got2))
         full_est, full_it, _ = oracle.em_batched(a, mode=oracle.MODE_SPARSE)
@@ -73,3 +83,12 @@ def test_sharded_groups_reassemble_world2():
 def test_shard_samples_partition():
     sh = bdist.shard_samples([5, 1, 9, 3, 3, 7, 2], 3)
     assert sorted(np.concatenate(sh).tolist()) == list(range(7))
+
+
+def test_shard_groups_by_weight_places_giants_first():
+    w = np.array([1, 2, 3_000_000, 5, 2_000_000, 7, 2_500_000, 1])
+    sh = bdist.shard_groups_by_weight(w, 3)
+    assert sorted(np.concatenate(sh).tolist()) == list(range(8))
+    assert sorted(int(np.argmax(w[x])) >= 0 for x in sh) and len({tuple(x) for x in sh}) == 3
+    heavy = [set(x) & {2, 4, 6} for x in sh]
+    assert all(len(h) == 1 for h in heavy)           # one giant locus per rank
