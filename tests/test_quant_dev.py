@@ -157,16 +157,20 @@ def test_hostexec_edge_cases(hx):
     dup = {"GENEID": [1, 1], "txid": [1, 1], "eqClassId": [7, 7], "nobs": [3.0, 3.0]}
     with pytest.raises(ValueError, match="duplicated"):
         hostexec_pack(hx, dup, False)
-    # wide id ranges (sort keys of up to 64 bits)
+    # wide id ranges (sort keys of up to 64 bits); txid stays inside R's integer range, which is what the arena carries
     tab = random_long_table(rng, n_genes=30)
-    tab["txid"] = [t * 1_000_003 - 2 ** 40 for t in tab["txid"]]
+    tab["txid"] = [t * 1_003 - 2 ** 30 for t in tab["txid"]]
     tab["eqClassId"] = [e * 7_000_000_007 for e in tab["eqClassId"]]
     tab["GENEID"] = [hash(g) % (2 ** 62) - 2 ** 61 for g in tab["GENEID"]]
     a = hostexec_pack(hx, tab, True)
-    # (txid is an int32 in the arena: compare everything but that column)
     b = Q.pack_quantDT_native(tab)
-    assert np.array_equal(a.arena.col_idx, b.arena.col_idx) and np.array_equal(a.out_txid, b.out_txid)
-    assert_same_doubles(a.arena.aval, b.arena.aval, "aval")
+    same_pack(a, b)
+    # a txid beyond int32 would be truncated in the arena and merged under a wrong id: both packers refuse it
+    wide = dict(tab, txid=[t + 2 ** 33 for t in tab["txid"]])
+    with pytest.raises(ValueError, match="32-bit"):
+        hostexec_pack(hx, wide, True)
+    with pytest.raises(ValueError, match="32-bit"):
+        Q.pack_quantDT_native(wide)
 
 
 # ---------------------------------------------------------------------------- the CUDA executor (B200)
