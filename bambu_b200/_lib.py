@@ -59,6 +59,8 @@ SYMBOLS = {
                                      ctypes.POINTER(_i64), ctypes.POINTER(_f64)]),
     "bambu_quantDT_hostpack": (ctypes.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _f64, _f64, _p, _p, _p, _p,
                                               ctypes.POINTER(_i64), ctypes.POINTER(_f64)]),
+    "bambu_quantDT_cohort": (ctypes.c_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _f64, _f64, _i64, _p, _p, _i32,
+                                            _p, _p, _p, _p]),
     "bambu_quantDT_dotC": (None, [_p] * 19),
     "bambu_quant_pack_create_gpu": (ctypes.c_int, [ctypes.POINTER(_p), _i64, _p, _p, _p, _p, _p, _p, _p, _i32,
                                                    ctypes.POINTER(_i32)]),

@@ -17,6 +17,7 @@
 #include <system_error>
 #include <thread>
 #include <type_traits>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/bambu_em.h"
@@ -32,6 +33,7 @@ __device__ __forceinline__ void qd_min(uint64_t *p, uint64_t v) { atomicMin(rein
 __device__ __forceinline__ void qd_max(uint64_t *p, uint64_t v) { atomicMax(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v); }
 
 #include "quant_dev.inl"
+#include "r_round.h"
 
 namespace qdcuda {
 
@@ -412,7 +414,7 @@ struct DevTable {          // the long table in device memory
 template <class IdT, class EqT>
 int run_device_pack(qdcuda::CudaExec &x, int64_t n, const IdT *gene, const IdT *tx, const IdT *eq,
                     const double *nobs, const EqT *equal, const double *rcw, const double *txl, bool d_mode,
-                    qd::Result &R)
+                    qd::Result &R, qdcuda::Workspace &ws = qdcuda::g_ws)
 {
     const size_t N = (size_t)n;
     qd::Input in;
@@ -421,7 +423,7 @@ int run_device_pack(qdcuda::CudaExec &x, int64_t n, const IdT *gene, const IdT *
     if (getenv("BAMBU_PACK_POISON"))      // debugging aid: nothing may depend on what the workspace held before
         QD_CUDA(cudaMemsetAsync(x.pool, 0xA5, x.cap, x.st));
     qdcuda::Uploader up;
-    for (int c = 0; c < qd::kNumCols; ++c) up.st[c] = qdcuda::g_ws.up_st[c];
+    for (int c = 0; c < qd::kNumCols; ++c) up.st[c] = ws.up_st[c];
     QD_CUDA(cudaGetDevice(&up.device));
     auto col = [&](int c, auto *src, bool wanted) -> decltype(src) {
         typedef typename std::remove_const<typename std::remove_pointer<decltype(src)>::type>::type T;
@@ -712,9 +714,12 @@ void bambu_quantDT_dotC(const int *n_rows, const int *gene_code, const int *txid
 
 }  // extern "C"
 
+#include "quant_cohort.inl"
+
 // releases the packer's cached device workspace (bambu_em_shutdown calls it)
 void bambu_quant_release_workspace()
 {
+    cohort_release();
     if (qdcuda::g_plan) bambu_em_plan_destroy(qdcuda::g_plan);
     qdcuda::g_plan = nullptr;
     qdcuda::g_ws.release();

@@ -57,9 +57,10 @@ class SharedHostTable:
     host over rank 0's link)."""
 
     def __init__(self, rows_local: int, group=None, pin: bool = True):
+        import mmap
+        import os
         import torch
         import torch.distributed as dist
-        from multiprocessing import shared_memory
         self.dist, self.group = dist, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         allr = [None] * self.world
@@ -67,23 +68,28 @@ class SharedHostTable:
         self.rows = [int(x) for x in allr]
         off = np.concatenate(([0], np.cumsum([3 * 8 * r for r in self.rows]))).astype(np.int64)
         self.total = int(max(off[-1], 8))
+        # a file in /dev/shm (tmpfs) mapped by every rank; rank 0 creates it, the name travels by broadcast
         name = [None]
         if self.rank == 0:
             try:
-                import os
                 st = os.statvfs("/dev/shm")
                 if st.f_bavail * st.f_frsize < self.total + (64 << 20):
                     raise OSError("not enough room in /dev/shm")
-                self.shm = shared_memory.SharedMemory(create=True, size=self.total)
-                name[0] = self.shm.name
+                path = "/dev/shm/bambu_b200_%d_%x" % (os.getpid(), int.from_bytes(os.urandom(4), "little"))
+                fd = os.open(path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+                os.ftruncate(fd, self.total)
+                os.close(fd)
+                name[0] = path
             except OSError:
                 name[0] = None
         dist.broadcast_object_list(name, src=0, group=group)
         if name[0] is None:        # every rank raises: the caller falls back to the NCCL gather
             raise RuntimeError("SharedHostTable: no shared memory for %d bytes" % self.total)
-        if self.rank != 0:
-            self.shm = shared_memory.SharedMemory(name=name[0])
-        buf = np.frombuffer(self.shm.buf, dtype=np.uint8, count=self.total)
+        self.path = name[0]
+        fd = os.open(self.path, os.O_RDWR)
+        self._map = mmap.mmap(fd, self.total)      # stays mapped until the process ends (numpy views point into it)
+        os.close(fd)
+        buf = np.frombuffer(self._map, dtype=np.uint8, count=self.total)
         self._views = [buf[off[r]:off[r + 1]].view(np.float64).reshape(3, self.rows[r]) for r in range(self.world)]
         self.mine = self._views[self.rank]
         self.mine[...] = 0.0                      # touch the pages from the rank that writes them
@@ -93,6 +99,11 @@ class SharedHostTable:
             self.pinned = int(rc) == 0
         self._buf = buf
         dist.barrier(group=group)
+        if self.rank == 0:                        # every rank has it mapped: the name can go
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
 
     def gather(self):
         """Every rank has finished writing its slice when this returns."""
@@ -103,20 +114,15 @@ class SharedHostTable:
         return self._views if self.rank == 0 else None
 
     def close(self):
+        """Unpins the table.  The mapping itself lives until the process ends (callers may still hold views)."""
         import torch
         try:
             if self.pinned:
                 torch.cuda.cudart().cudaHostUnregister(self._buf.ctypes.data)
+                self.pinned = False
         except Exception:
             pass
         self.dist.barrier(group=self.group)
-        self._views = self.mine = self._buf = None
-        try:
-            self.shm.close()
-            if self.rank == 0:
-                self.shm.unlink()
-        except Exception:
-            pass
 
 
 def gather_estimates(est, device=None, dst=0, group=None):

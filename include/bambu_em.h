@@ -260,6 +260,28 @@ void bambu_quantDT_dotC(const int *n_rows, const int *gene_code, const int *txid
                         const int *degradation_bias, const int *maxiter, const double *minvalue, const double *conv,
                         int *txid_out, double *counts, double *full_length, double *unique_counts, int *n_result,
                         double *d_rate, int *rc);
+/* ---- the quantification stage of a whole cohort: bplapply(readClassList, bambu.quantify) + combineCountSes ------
+ * (R/bambu.R:187-192, R/bambu-quantify.R:22-38, R/bambu_utilityFunctions.R:215-241) for the part after genEquiRCs.
+ * Per sample s: the long table (n_rows[s] rows; column pointers [s], as bambu_quantDT takes them; equal / rcWidth /
+ * txlen may be NULL arrays) is copied to the GPU and packed there, the EM runs on the arena in HBM, and the epilogue --
+ * modifyQuantOut, removeDuplicates, calculateCPM (denominator = sum(counts) + incompatible_total[s], R's long double
+ * sum, result-row order), counts[match(annotation_txid, txid)], round(., sig_digit) of counts / CPM / fullLengthCounts
+ * -- runs on the device and writes the sample's column of the four assays.  Samples are spread over a few worker
+ * threads (BAMBU_COHORT_WORKERS, default 3) so that copies, packing and EM of different samples overlap.
+ *
+ *   assays         HOST, 4 * n_samples * n_tx doubles (may be NULL): assays[(k * n_samples + s) * n_tx + a], k = 0 counts,
+ *                  1 CPM, 2 fullLengthCounts, 3 uniqueCounts -- i.e. four column-major n_tx x n_samples R matrices;
+ *                  annotation transcripts the sample's table never mentions are NA (NaN), as match() leaves them
+ *   assays_device  the same block in DEVICE memory (may be NULL): what a multi-GPU run gathers
+ *   d_rate         [n_samples] degradation rate of each sample (may be NULL)
+ *   used_device    [n_samples] 1, or 0 for a sample that went through the host packer (see bambu_quantDT_hostpack)
+ * Table buffers may be pageable; page-locked ones (cudaHostRegister / cudaMallocHost) copy about 5x faster. */
+int bambu_quantDT_cohort(int32_t n_samples, const int64_t *n_rows, const int64_t *const *gene_code,
+                         const int64_t *const *txid, const int64_t *const *eqClassId, const double *const *nobs,
+                         const uint8_t *const *equal, const double *const *rcWidth, const double *const *txlen,
+                         int32_t degradation_bias, int32_t maxiter, double minvalue, double conv, int64_t n_tx,
+                         const int64_t *annotation_txid, const double *incompatible_total, int32_t sig_digit,
+                         double *assays, double *assays_device, double *d_rate, int32_t *used_device);
 /* bambu_quant_pack_create done by the GPU (csrc/quant_dev.cu), the arena copied back into a host pack object.
  * used_device (may be NULL) receives 1, or 0 when the table went through the host packer (see above). */
 int bambu_quant_pack_create_gpu(bambu_quant_pack **pack, int64_t n_rows, const int64_t *gene_code, const int64_t *txid,
