@@ -376,6 +376,68 @@ def bambu_quantDT_native(readClassDt, emParameters=None, host_pack=False):
             "d_rate": float(d.value)}
 
 
+def bambu_quantDT_cohort_native(tables, annotation_txid, incompatible_totals=None, emParameters=None, sig_digit=5,
+                                device_assays=None):
+    """The quantification stage of a cohort in ONE library call (``bambu_quantDT_cohort``): what ``bambu()`` does with
+    ``bplapply(readClassList, bambu.quantify)`` + ``combineCountSes`` (R/bambu.R:187-192) after ``genEquiRCs`` --
+    per sample ``bambu.quantDT``, ``calculateCPM``, ``counts[match(annotation txid, txid)]``, ``round(., sig.digit)``.
+
+    ``tables``: list of long tables (dicts as :func:`bambu_quantDT` takes them; GENEID already integer-coded or any
+    hashable); ``incompatible_totals[s]`` = ``sum(incompatibleCounts$counts)`` of sample s.  Returns a dict of four
+    ``n_tx x n_samples`` matrices (Fortran order, like R) plus ``d_rate`` and ``used_device`` per sample.
+    ``device_assays``: optional raw device address of a ``4 * n_samples * n_tx`` float64 block to fill as well."""
+    import ctypes
+    from . import _lib
+    par = setEmParameters(emParameters)
+    L = _lib.lib()
+    S = len(tables)
+    ann = np.ascontiguousarray(annotation_txid, dtype=np.int64)
+    T = len(ann)
+    c = lambda a, dt: np.ascontiguousarray(np.asarray(a), dtype=dt)      # noqa: E731
+    keep, cols = [], {k: [] for k in ("gene", "tx", "eq", "nobs", "equal", "rcw", "txl")}
+    n_rows = np.zeros(max(S, 1), np.int64)
+    have = {k: True for k in ("equal", "rcw", "txl")}
+    for s, tab in enumerate(tables):
+        if tab is None or any(k not in tab for k in ("GENEID", "txid", "eqClassId", "nobs")):
+            raise ValueError("Columns GENEID, txid, eqClassId, nobs, are missing from object.")
+        n_rows[s] = len(tab["txid"])
+        g = tab["GENEID"]
+        gene = g if isinstance(g, np.ndarray) and g.dtype == np.int64 and g.flags.c_contiguous else _gene_codes(g)
+        arrs = {"gene": gene, "tx": c(tab["txid"], np.int64), "eq": c(tab["eqClassId"], np.int64), "nobs": c(tab["nobs"], np.float64),
+                "equal": c(np.asarray(tab["equal"], dtype=bool), np.uint8) if "equal" in tab else None,
+                "rcw": c(tab["rcWidth"], np.float64) if "rcWidth" in tab else None,
+                "txl": c(tab["txlen"], np.float64) if "txlen" in tab else None}
+        for k, v in arrs.items():
+            cols[k].append(v)
+            if v is None:
+                have[k] = False
+        keep.append(arrs)
+
+    def ptr_array(vs):
+        arr = (ctypes.c_void_p * max(S, 1))()
+        for i, v in enumerate(vs):
+            arr[i] = v.ctypes.data if v is not None else None
+        return arr
+    pa = {k: ptr_array(v) for k, v in cols.items()}
+    if S and len({v is None for v in cols["equal"]}) > 1:
+        raise ValueError("either every table carries an `equal` column or none does")
+    assays = np.zeros((4, max(S, 1), max(T, 1)), dtype=np.float64)
+    d_rate = np.zeros(max(S, 1), np.float64)
+    used = np.zeros(max(S, 1), np.int32)
+    inc = np.zeros(max(S, 1), np.float64) if incompatible_totals is None else c(incompatible_totals, np.float64)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)      # noqa: E731
+    rc = L.bambu_quantDT_cohort(S, vp(n_rows), pa["gene"], pa["tx"], pa["eq"], pa["nobs"],
+                                pa["equal"] if have["equal"] else None, pa["rcw"] if have["rcw"] else None,
+                                pa["txl"] if have["txl"] else None, int(bool(par["degradationBias"])), int(par["maxiter"]),
+                                float(par["minvalue"]), float(par["conv"]), T, vp(ann), vp(inc), int(sig_digit), vp(assays),
+                                ctypes.c_void_p(int(device_assays)) if device_assays else None, vp(d_rate), vp(used))
+    _lib.check_quant(rc)
+    names = ("counts", "CPM", "fullLengthCounts", "uniqueCounts")
+    out = {n: np.asfortranarray(assays[k, :S, :T].T) for k, n in enumerate(names)}
+    out["d_rate"], out["used_device"] = d_rate[:S], used[:S]
+    return out
+
+
 # ------------------------------------------------------------------ the stage
 def bambu_quantDT(readClassDt, emParameters=None, verbose=False, em=None, details=None):
     """``bambu.quantDT`` (R/bambu-quantify.R:53-74).
@@ -428,5 +490,5 @@ def calculateCPM(counts, incompatibleCounts=0.0):
     counts = np.asarray(counts, dtype=np.float64)
     inc = np.atleast_1d(np.asarray(incompatibleCounts, dtype=np.float64))
     seq = lambda v: (np.cumsum(v.astype(LD))[-1] if len(v) else LD(0))   # sequential, like R  # noqa: E731
-    tot = float(seq(counts) + seq(inc))
+    tot = float(seq(counts)) + float(seq(inc))      # each sum() returns a double; `+` is then a double addition
     return counts / tot * 1e6
