@@ -9,6 +9,7 @@
 // slot over the whole arena; bambu_em_batched() streams the arena through three
 // cached slots so that copies and kernels of neighbouring chunks overlap.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -917,7 +918,8 @@ struct bambu_em_plan {
     int64_t n_groups = 0;
 };
 
-static Slot g_pipe[3];            // cached slots of bambu_em_batched
+constexpr int kPipeSlots = 3;
+static Slot g_pipe[kPipeSlots];   // cached slots of bambu_em_batched
 static bool g_pipe_used = false;
 
 extern "C" {
@@ -1211,7 +1213,7 @@ static int batched_impl(int64_t n_groups, const int64_t *grp_row_ptr, const int6
             bytes += 13 * e + 17 * cols + 8 * rows + 16;
             ++g1;
         }
-        Slot &s = g_pipe[k % 3];
+        Slot &s = g_pipe[k % kPipeSlots];
         ++k;
         rc = collect(s);                        // the slot's previous chunk (its D2H is then ordered on its stream)
         if (rc) break;
@@ -1251,6 +1253,12 @@ static int batched_impl_v2(int64_t n_groups, const int64_t *grp_row_ptr, const i
     int rc = BAMBU_EM_OK;
     int64_t g0 = 0, ib0 = 0;
     int k = 0;
+    // BAMBU_EM_TIMING=1: where the host thread of this call spends its time (stderr, one line per call)
+    const bool timing = getenv("BAMBU_EM_TIMING") != nullptr;
+    double t_collect = 0, t_prepare = 0, t_upload = 0, t_run = 0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+    const auto t_call = now();
     while (g0 < n_groups && !rc) {
         const int64_t ramp = (int64_t)12 << (20 + (k < 6 ? k : 6));       // 12 MB doubling: the wire form is ~1/3 of v1
         const int64_t target = ramp < target_max ? ramp : target_max;
@@ -1261,14 +1269,22 @@ static int batched_impl_v2(int64_t n_groups, const int64_t *grp_row_ptr, const i
             bytes += (8 + wire_idx_width(cols)) * e + colb * cols + 12 * rows + 32;
             ++g1;
         }
-        Slot &s = g_pipe[k % 3];
+        Slot &s = g_pipe[k % kPipeSlots];
         ++k;
+        auto t0 = now();
         rc = collect(s);
+        t_collect += since(t0);
         if (rc) break;
         s.single_tx_shortcut = true;
+        t0 = now();
         rc = slot_prepare(s, grp_row_ptr, grp_col_ptr, nullptr, g0, g1, grp_ent_ptr, ib0);
+        t_prepare += since(t0);
+        t0 = now();
         if (!rc) rc = slot_upload_v2(s, h);
+        t_upload += since(t0);
+        t0 = now();
         if (!rc) rc = slot_run(s, maxiter, minvalue, conv);
+        t_run += since(t0);
         if (!rc) {
             s.busy = true;
             s.dl_est = est; s.dl_iters = iters; s.dl_status = status; s.dl_total_rows = total_rows;
@@ -1276,6 +1292,7 @@ static int batched_impl_v2(int64_t n_groups, const int64_t *grp_row_ptr, const i
         }
         g0 = g1;
     }
+    const auto t_drain = now();
     for (Slot &s : g_pipe) {
         int rc2 = collect(s);
         if (!rc) rc = rc2;
@@ -1283,6 +1300,9 @@ static int batched_impl_v2(int64_t n_groups, const int64_t *grp_row_ptr, const i
     for (Slot &s : g_pipe)
         if (s.inited && cudaStreamSynchronize(s.stream) != cudaSuccess && !rc)
             rc = fail(BAMBU_EM_ECUDA, "pipeline stream failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (timing)
+        fprintf(stderr, "[bambu_em_batched_v2] %d chunks, %.1f ms: wait for a free slot %.1f, analyse %.1f, enqueue copies %.1f, "
+                        "enqueue kernels %.1f, drain %.1f\n", k, since(t_call), t_collect, t_prepare, t_upload, t_run, since(t_drain));
     if (n_groups == 0) return BAMBU_EM_OK;
     return rc;
 }
