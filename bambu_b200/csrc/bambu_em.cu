@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "em_sell.cuh"
 #include "giant.cuh"
+#include "giant_pack.cuh"
 #include "pack_kernel.cuh"
 #include "sell_kernel.cuh"
 
@@ -202,7 +203,7 @@ struct Slot {
     int32_t col_mode = 0;
     // device buffers (grow-only)
     DevBuf grp_row_ptr, grp_col_ptr, row_nnz_ptr, payload, img, img_off, info, pool, ginfo, queue, nnz_nonzero, est,
-        iters, status, work, ctrl, gdesc, gbuf, grp_idx_off;
+        iters, status, work, ctrl, gdesc, gbuf, grp_idx_off, ghist;
     // per-group extents of the current chunk (host copy: the caller's arrays may be gone by the time a
     // group has to be moved to the streamed tier)
     std::vector<int32_t> hM, hN;
@@ -289,7 +290,7 @@ static void slot_destroy(Slot &s)
     if (s.own_stream) cudaStreamDestroy(s.own_stream);
     for (DevBuf *b : {&s.grp_row_ptr, &s.grp_col_ptr, &s.row_nnz_ptr, &s.payload, &s.img, &s.img_off, &s.info, &s.pool,
                       &s.ginfo, &s.queue, &s.nnz_nonzero, &s.est, &s.iters, &s.status, &s.work, &s.ctrl, &s.gdesc, &s.gbuf,
-                      &s.grp_idx_off})
+                      &s.grp_idx_off, &s.ghist})
         b->release();
     s.h_idx_off.release();
     s.h_gdesc.release();
@@ -707,6 +708,31 @@ static int slot_upload_v2(Slot &s, const WireHost &h)
 // ---- streamed tier launches over descs [first, first + count) ---------------------------------
 static int launch_giant_pack(Slot &s, const SlotViews &v, int first, int count, cudaStream_t st)
 {
+    if (s.v2 && !getenv("BAMBU_EM_GIANT_PACK_1CTA")) {
+        // wire form v2: every phase is a flat grid over (locus, tile) -- the whole GPU packs (giant_pack.cuh)
+        GiantDesc *d = s.gdesc.as<GiantDesc>() + first;
+        uint8_t *gb = s.gbuf.as<uint8_t>();
+        TRY(s.ghist.ensure(4 * 1024 * (size_t)count, &s.device_bytes));
+        uint32_t *hist = s.ghist.as<uint32_t>();
+        CUDA_TRY(cudaMemsetAsync(hist, 0, 4 * 1024 * (size_t)count, st));
+        const int tiles = std::max(1, std::min(1024, (8 * g_num_sms + count - 1) / count));
+        const dim3 flat((unsigned)tiles, (unsigned)count), one(1, (unsigned)count);
+        gp_cols<<<flat, kGpThreads, 0, st>>>(v.W, d, gb);
+        gp_rowcount<<<flat, kGpThreads, 0, st>>>(v.W, d, gb, &v.ctrl->err);
+        gp_scan_rows<<<one, 1024, 0, st>>>(d, gb, v.nnz_nonzero, v.W);
+        gp_rowfill<<<flat, kGpThreads, 0, st>>>(v.W, d, gb, &v.ctrl->err);
+        gp_scan_cols<<<one, 1024, 0, st>>>(d, gb);
+        gp_scatter<<<flat, kGpThreads, 0, st>>>(d, gb);
+        gp_sortcols<<<flat, kGpThreads, 0, st>>>(d, gb, hist);
+        gp_sell_scan_hist<<<one, 1024, 0, st>>>(hist);
+        gp_sell_place<<<flat, kGpThreads, 0, st>>>(d, gb, hist);
+        gp_sell_slices<<<flat, kGpThreads, 0, st>>>(d, gb);
+        gp_sell_scan_slices<<<one, 1024, 0, st>>>(d, gb);
+        gp_sell_fill<<<flat, kGpThreads, 0, st>>>(d, gb);
+        CUDA_TRY(cudaGetLastError());
+        s.launches += 12;
+        return BAMBU_EM_OK;
+    }
     if (s.v2)
         pack_giant_kernel<1024, true><<<count, 1024, 0, st>>>(v.A, v.W, s.gdesc.as<GiantDesc>() + first, count,
                                                                s.gbuf.as<uint8_t>(), v.nnz_nonzero, &v.ctrl->err);
@@ -1266,7 +1292,10 @@ static int batched_impl_v2(int64_t n_groups, const int64_t *grp_row_ptr, const i
         while (g1 < n_groups && (g1 == g0 || bytes < target)) {
             const int64_t rows = grp_row_ptr[g1 + 1] - grp_row_ptr[g1], cols = grp_col_ptr[g1 + 1] - grp_col_ptr[g1];
             const int64_t e = grp_ent_ptr[g1 + 1] - grp_ent_ptr[g1];
-            bytes += (8 + wire_idx_width(cols)) * e + colb * cols + 12 * rows + 32;
+            const int64_t gb = (8 + wire_idx_width(cols)) * e + colb * cols + 12 * rows + 32;
+            // giant loci iterate for long (their copy is small next to their EM) and a chunk's cooperative launch ends
+            // with its slowest team: count them at a quarter of their size so that more of them share a chunk
+            bytes += (e > 200000) ? gb / 4 : gb;
             ++g1;
         }
         Slot &s = g_pipe[k % kPipeSlots];

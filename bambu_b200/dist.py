@@ -49,12 +49,19 @@ def shard_groups_by_weight(entries, world, expected_iters=None):
 
 
 class SharedHostTable:
-    """The combined estimate table of a one-box run, gathered on the HOST side: one POSIX shared-memory segment
-    that every rank maps (and page-locks when CUDA is there).  A rank's C-ABI call downloads its ``est[3, rows_r]``
-    straight into its slice over its own PCIe link; ``gather()`` is then only a barrier, after which rank 0 holds
-    every rank's table (``tables()``) -- the reference's ``combineCountSes`` cbind (R/bambu_utilityFunctions.R:215-241)
-    without a second pass over any link.  ``EstimateGatherer`` is the NCCL alternative (tables travel GPU -> GPU 0 ->
-    host over rank 0's link)."""
+    """The combined estimate table of a one-box run, gathered on the HOST side: one file in /dev/shm that every rank
+    maps.  A rank's C-ABI call downloads its ``est[3, rows_r]`` straight into its own slice (page-locked, over its own
+    PCIe link) and then *publishes* the step by bumping its counter in the table's header; rank 0 *collects* a step by
+    waiting until every counter has reached it -- after which it holds every rank's table, which is the reference's
+    ``combineCountSes`` cbind (R/bambu_utilityFunctions.R:215-241) without a second pass over any link and without an
+    all-rank barrier on the critical path (only rank 0 waits; the others go on with their next step).  The table is
+    double-buffered: step k uses buffer k % 2, and a rank starting step k first waits until rank 0 has published its
+    own step k - 1 (by then rank 0's caller has finished reading step k - 2, the buffer's previous content).  ``EstimateGatherer`` is the NCCL alternative (tables travel GPU -> GPU 0 -> host over rank 0's link).
+
+    Layout: header of world + 1 cache lines (one int64 counter each: rank r's published step), then 2 buffers of all
+    ranks' slices."""
+
+    LINE = 64
 
     def __init__(self, rows_local: int, group=None, pin: bool = True):
         import mmap
@@ -66,9 +73,12 @@ class SharedHostTable:
         allr = [None] * self.world
         dist.all_gather_object(allr, int(rows_local), group=group)
         self.rows = [int(x) for x in allr]
-        off = np.concatenate(([0], np.cumsum([3 * 8 * r for r in self.rows]))).astype(np.int64)
-        self.total = int(max(off[-1], 8))
-        # a file in /dev/shm (tmpfs) mapped by every rank; rank 0 creates it, the name travels by broadcast
+        sizes = [3 * 8 * r for r in self.rows]
+        self.header = self.LINE * (self.world + 1)
+        off = self.header + np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
+        self.buf_bytes = int(sum(sizes))
+        self.total = int(self.header + 2 * max(self.buf_bytes, 8))
+        # rank 0 creates the file, the name travels by broadcast
         name = [None]
         if self.rank == 0:
             try:
@@ -77,7 +87,7 @@ class SharedHostTable:
                     raise OSError("not enough room in /dev/shm")
                 path = "/dev/shm/bambu_b200_%d_%x" % (os.getpid(), int.from_bytes(os.urandom(4), "little"))
                 fd = os.open(path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
-                os.ftruncate(fd, self.total)
+                os.ftruncate(fd, self.total)      # zero-filled: every counter starts at 0
                 os.close(fd)
                 name[0] = path
             except OSError:
@@ -90,14 +100,20 @@ class SharedHostTable:
         self._map = mmap.mmap(fd, self.total)      # stays mapped until the process ends (numpy views point into it)
         os.close(fd)
         buf = np.frombuffer(self._map, dtype=np.uint8, count=self.total)
-        self._views = [buf[off[r]:off[r + 1]].view(np.float64).reshape(3, self.rows[r]) for r in range(self.world)]
-        self.mine = self._views[self.rank]
-        self.mine[...] = 0.0                      # touch the pages from the rank that writes them
-        self.pinned = False
-        if pin and torch.cuda.is_available():
-            rc = torch.cuda.cudart().cudaHostRegister(buf.ctypes.data, self.total, 0)
-            self.pinned = int(rc) == 0
         self._buf = buf
+        self._ctr = buf[:self.header].view(np.int64)             # counter of rank r at index r * LINE / 8
+        self._views = [[buf[off[r] + b * self.buf_bytes: off[r + 1] + b * self.buf_bytes].view(np.float64).reshape(3, self.rows[r])
+                        for r in range(self.world)] for b in (0, 1)]
+        self.step = 0                                            # steps this rank has published
+        self._pinned = []
+        for b in (0, 1):                                         # first touch + page-lock of this rank's own slices only
+            mine = self._views[b][self.rank]
+            mine[...] = 0.0
+            if pin and torch.cuda.is_available() and mine.nbytes:
+                rc = torch.cuda.cudart().cudaHostRegister(mine.ctypes.data, mine.nbytes, 0)
+                if int(rc) == 0:
+                    self._pinned.append(mine.ctypes.data)
+        self.pinned = len(self._pinned) > 0
         dist.barrier(group=group)
         if self.rank == 0:                        # every rank has it mapped: the name can go
             try:
@@ -105,23 +121,54 @@ class SharedHostTable:
             except OSError:
                 pass
 
-    def gather(self):
-        """Every rank has finished writing its slice when this returns."""
-        self.dist.barrier(group=self.group)
-        return self.tables()
+    def _counter(self, r):
+        return int(self._ctr[r * self.LINE // 8])
 
-    def tables(self):
-        return self._views if self.rank == 0 else None
+    def _spin(self, cond):
+        import time
+        n = 0
+        while not cond():
+            n += 1
+            if n > 200:
+                time.sleep(20e-6)
+
+    @property
+    def mine(self):
+        """this rank's slice for its NEXT step; blocks while rank 0 still owns that buffer (step - 2 not collected)"""
+        k = self.step + 1
+        if k > 2 and self.rank != 0:
+            # buffer k % 2 last held step k - 2; rank 0's caller is done reading it once rank 0 has published step k - 1
+            self._spin(lambda: self._counter(0) >= k - 1)
+        return self._views[k % 2][self.rank]
+
+    def publish(self):
+        """this rank's table of the step is complete in host memory"""
+        self.step += 1
+        self._ctr[self.rank * self.LINE // 8] = self.step
+
+    def collect(self):
+        """rank 0: wait for every rank's table of the step this rank has just published, mark it collected and return
+        the per-rank views; other ranks return None at once"""
+        if self.rank != 0:
+            return None
+        k = self.step
+        self._spin(lambda: all(self._counter(r) >= k for r in range(self.world)))
+        return self._views[k % 2]
+
+    def gather(self):
+        """publish + collect: the host-side gather of one step"""
+        self.publish()
+        return self.collect()
 
     def close(self):
-        """Unpins the table.  The mapping itself lives until the process ends (callers may still hold views)."""
+        """Unpins the slices.  The mapping itself lives until the process ends (callers may still hold views)."""
         import torch
-        try:
-            if self.pinned:
-                torch.cuda.cudart().cudaHostUnregister(self._buf.ctypes.data)
-                self.pinned = False
-        except Exception:
-            pass
+        for p in self._pinned:
+            try:
+                torch.cuda.cudart().cudaHostUnregister(p)
+            except Exception:
+                pass
+        self._pinned = []
         self.dist.barrier(group=self.group)
 
 

@@ -290,9 +290,13 @@ class HostGather:
             from bambu_b200 import dist as bdist
             self.nccl = bdist.EstimateGatherer(rows, ctx.dev)
             self.buf = ctx.torch.empty((3, rows), dtype=ctx.torch.float64, pin_memory=True)
-        self.mine = self.table.mine if self.table is not None else self.buf.numpy()
         self.kind = ("host side: every rank's D2H lands in one shared, page-locked table (dist.SharedHostTable)"
                      if self.table is not None else "NCCL gather to GPU 0 + D2H (no shared memory available)")
+
+    @property
+    def mine(self):
+        """host buffer for this rank's tables of its NEXT step (the shared table is double-buffered)"""
+        return self.table.mine if self.table is not None else self.buf.numpy()
 
     def gather(self):
         if self.table is not None:
@@ -418,6 +422,7 @@ def cohort_strong(ctx, args, slab0, t1_dev_ms, t1_e2e_ms):
     dev_ms = ctx.reduce([slab.run_device(3, 1) / 3.0])[0]
 
     def step():
+        slab.h_est = table.mine
         slab.e2e_call()
         table.gather()
     e2e_ms = timed_e2e(ctx, step, 3, 2) / 3.0 * 1e3
@@ -462,6 +467,7 @@ def config3_block(ctx, args):
             pack = ctx.reduce([slab.plan.last_run_ms()["pack_ms"]])[0]
 
             def step():
+                slab.h_est = table.mine
                 slab.e2e_call()
                 table.gather()
             e2e = timed_e2e(ctx, step, 2, 1) / 2.0 * 1e3
@@ -584,6 +590,8 @@ def run_b200(args):
     # ranks are on rank 0's host when the step ends (the reference's combineCountSes cbind): each rank's D2H lands in
     # a shared page-locked table, the gather itself is a barrier
     def e2e_step():
+        if table is not None:
+            slab.h_est = table.mine
         slab.e2e_call()
         if table is not None:
             table.gather()
@@ -643,8 +651,8 @@ def run_b200(args):
                     "api": "bambu_em_batched_v2 (wire form v2 of the arena: live entries + rs, %.0f %% of the v1 arena's "
                            "%d bytes per rank)" % (100.0 * h2d / v1_bytes, v1_bytes),
                     "timer": "host wall clock around the C-ABI call (plan + H2D + kernels + D2H"
-                             + ("; every rank's D2H lands in one shared page-locked table on the host = the gather to rank 0, "
-                                "closed by a barrier per step)" if world > 1 else ")"),
+                             + ("; every rank's D2H lands in its slice of one shared, double-buffered host table and is "
+                                "published by a counter; rank 0 waits for all counters = the gather to rank 0)" if world > 1 else ")"),
                     "one_gpu_ms_per_step": solo_e2e_ms, "nccl_gather_ms_per_step": nccl_e2e_ms},
             "stages_ms": stages,
             "gpu_launches": int(slab.launches * args.steps),

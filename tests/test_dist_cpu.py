@@ -44,12 +44,13 @@ def _worker(rank, world, port, q):
     got2 = g2(np.ascontiguousarray(est))
     # host-side gather: every rank writes its slice of one shared-memory table, rank 0 reads all of them
     tab = bdist.SharedHostTable(est.shape[1])
-    tab.mine[...] = est
-    got3 = tab.gather()
-    if rank == 0:
-        assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(got, got3))
-    else:
-        assert got3 is None
+    for step in range(1, 6):          # double-buffered: a rank may run ahead of rank 0 by at most two steps
+        tab.mine[...] = est * step
+        got3 = tab.gather()
+        if rank == 0:
+            assert all(np.array_equal(x * step, y, equal_nan=True) for x, y in zip(got, got3))
+        else:
+            assert got3 is None
     got3 = None
     tab.close()
     if rank == 0:

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--samples", type=int, default=50)
     ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
     ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--chunks", action="store_true", help="also sweep the chunk size")
     args = ap.parse_args()
     ctx = bench.Ctx(args)
     arena = bench.make_cohort(range(ctx.rank * args.samples, (ctx.rank + 1) * args.samples), args.scale)
@@ -61,10 +62,32 @@ def main():
             print(f"    e2e per step: slowest rank {mx:.1f} ms, fastest {mn:.1f} ms", flush=True)
 
     run("rank 0 alone, default chunks", {"BAMBU_EM_CHUNK_MB": None}, solo=True)
-    run("all ranks, default chunks (96 MB)", {"BAMBU_EM_CHUNK_MB": None})
-    run("all ranks, 32 MB chunks", {"BAMBU_EM_CHUNK_MB": "32"})
-    run("all ranks, 256 MB chunks", {"BAMBU_EM_CHUNK_MB": "256"})
-    run("all ranks, 1 GB chunks", {"BAMBU_EM_CHUNK_MB": "1024"})
+    run("all ranks, default chunks (96 MB), tables into torch-pinned memory", {"BAMBU_EM_CHUNK_MB": None})
+    if args.chunks:
+        run("all ranks, 32 MB chunks", {"BAMBU_EM_CHUNK_MB": "32"})
+        run("all ranks, 256 MB chunks", {"BAMBU_EM_CHUNK_MB": "256"})
+    if ctx.world > 1:
+        # the bench's gather target: one shared, page-locked table in /dev/shm
+        gather = bench.HostGather(ctx, slab.rows)
+        keep = slab.h_est
+        call = slab.e2e_call
+
+        def with_gather():
+            slab.h_est = gather.mine
+            call()
+            gather.gather()
+        slab.e2e_call = with_gather
+        run("all ranks, tables into the shared host table, published by counters (what bench.py times)", {"BAMBU_EM_CHUNK_MB": None})
+        slab.e2e_call = call
+        slab.h_est = keep
+
+        def pinned_with_barrier():
+            call()
+            ctx.barrier()
+        slab.e2e_call = pinned_with_barrier
+        run("all ranks, torch-pinned tables + barrier per step", {"BAMBU_EM_CHUNK_MB": None})
+        slab.e2e_call = call
+        gather.close()
     # copies alone, the way the library issues them (plan upload = one cudaMemcpyAsync per array of the whole slab)
     torch = ctx.torch
     for label, fn in (("upload of the whole wire slab (plan API), all ranks", slab.upload),):
