@@ -658,7 +658,7 @@ def run_b200(args):
             "gpu_launches": int(slab.launches * args.steps),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (cap or {}).get("dram_bytes_per_step"),
+                         "traffic": ((cap or {}).get("dram_bytes_per_sample") or 0) * args.samples * args.scale or None,
                          "binding": (cap or {}).get("binding"),
                          "capture": (cap or {}).get("capture"),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
