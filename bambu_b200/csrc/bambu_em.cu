@@ -123,6 +123,9 @@ static const EmClass kEmClasses[kNumClasses] = {
     {kSmemMax, 1024},      // 1
 };
 static int g_em_grid[kNumClasses] = {};
+static int g_em_grid_lat[kNumClasses] = {};     // latency instance (256 threads, 4 slots in flight) on the classes below 256 threads
+constexpr int kLatThreads = 256, kLatUnroll = 4;
+constexpr int kLatClasses = 3;                  // classes 0..2 (64 / 64 / 128 threads in throughput mode)
 static bool g_em_configured = false;
 
 struct Ctrl {   // device control block, zeroed at the start of every run
@@ -322,6 +325,19 @@ static int em_config_T(int c)
     return BAMBU_EM_OK;
 }
 
+static int em_config_latency()
+{
+    auto em = em_sell_kernel<kLatThreads, kLatUnroll>;
+    CUDA_TRY(cudaFuncSetAttribute(em, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmClasses[kLatClasses - 1].max_bytes));
+    for (int c = 0; c < kLatClasses; ++c) {
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em, kLatThreads, kEmClasses[c].max_bytes));
+        if (per_sm < 1) return fail(BAMBU_EM_ECUDA, "latency EM kernel does not fit an SM (class %d)", c);
+        g_em_grid_lat[c] = per_sm * g_num_sms;
+    }
+    return BAMBU_EM_OK;
+}
+
 template <int T>
 static int pack_config_T()
 {
@@ -353,6 +369,7 @@ static int configure_kernels()
         default: return fail(BAMBU_EM_EINVAL, "no EM kernel instance for %d threads", kEmClasses[c].threads);
         }
     }
+    TRY(em_config_latency());
     TRY(pack_config_T<64>());
     TRY(pack_config_T<128>());
     TRY(pack_config_T<256>());
@@ -446,8 +463,24 @@ static int launch_pack(Slot &s, int bi, const SlotViews &v)
     return fail(BAMBU_EM_EINVAL, "no pack kernel instance for %d threads", kPackClasses[bi].threads);
 }
 
+// A small arena (a single sample, a few samples) is bound by its longest-running groups, not by residency: its small
+// classes run on the latency instance of the kernel.  BAMBU_EM_LATENCY_GROUPS moves the threshold (0 = never).
+static bool latency_mode(const Slot &s)
+{
+    const char *e = getenv("BAMBU_EM_LATENCY_GROUPS");
+    return s.ng() <= (e ? atoll(e) : (int64_t)16384);
+}
+
 static int launch_em(Slot &s, int c, const SlotViews &v)
 {
+    if (c < kLatClasses && latency_mode(s)) {
+        em_sell_kernel<kLatThreads, kLatUnroll><<<g_em_grid_lat[c], kLatThreads, kEmClasses[c].max_bytes, s.em_stream[c]>>>(
+            s.queue.as<int32_t>() + (int64_t)c * std::max<int64_t>(s.ng(), 1), v.ctrl->qcount + c, v.ctrl->ticket + c, v.ginfo,
+            s.pool.as<uint8_t>(), v.A.grp_row_ptr, s.rows(), s.P, v.est, v.iters, v.status);
+        CUDA_TRY(cudaGetLastError());
+        s.launches += 1;
+        return BAMBU_EM_OK;
+    }
     switch (kEmClasses[c].threads) {
     case 64: return launch_em_T<64>(s, c, v);
     case 128: return launch_em_T<128>(s, c, v);

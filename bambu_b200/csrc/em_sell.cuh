@@ -70,12 +70,12 @@ __device__ __forceinline__ double vec_at(const uint8_t *vec, uint32_t off)
     return *reinterpret_cast<const double *>(vec + off);
 }
 
-template <int MODE>
+template <int MODE, int U = kSlotUnroll>
 __device__ __forceinline__ void line_sums(const uint8_t *__restrict__ side, uint2 desc, int lane,
                                           const uint8_t *__restrict__ vec, double &a1, double &a2, int &cnt)
 {
     const uint8_t *p = side + desc.x;        // desc = {byte offset of the slice's first slot, slots}
-#pragma unroll kSlotUnroll
+#pragma unroll U
     for (uint32_t s = 0; s < desc.y; ++s, p += kSlotBytes) {
         const double2 v = reinterpret_cast<const double2 *>(p)[lane];
         const uint32_t oe = reinterpret_cast<const uint16_t *>(p + 512)[lane];
@@ -91,7 +91,11 @@ __device__ __forceinline__ void line_sums(const uint8_t *__restrict__ side, uint
 #define BAMBU_V_LAZY 1
 #endif
 
-template <int T>
+// T threads per CTA; U = slots of a line in flight per lane.  The throughput instances (U = 1: 64 / 128 threads for the
+// small classes) keep as many groups resident per SM as registers and shared memory allow; the latency instance
+// (256 threads, U = 4: one slice per warp, the loads of four slots in flight) gives ONE group a short update and is
+// what a small arena -- a single sample -- runs on, where the longest-running groups bound the run time.
+template <int T, int U = kSlotUnroll>
 __global__ void __launch_bounds__(T)
 em_sell_kernel(const int32_t *__restrict__ queue, const int *__restrict__ qcount, int *__restrict__ ticket,
                const GroupImg *__restrict__ ginfo, const uint8_t *__restrict__ pool,
@@ -186,7 +190,7 @@ em_sell_kernel(const int32_t *__restrict__ queue, const int *__restrict__ qcount
                 double a1 = 0.0, a2 = 0.0;
                 int cnt = 0;
                 if (nP == 0) {
-                    line_sums<0>(sideC, descC[sl], lane, vec, a1, a2, cnt);
+                    line_sums<0, U>(sideC, descC[sl], lane, vec, a1, a2, cnt);
                 } else {
                     // dense semantics: a row with non-finite theta poisons every column it has a
                     // structural zero in (0*NaN), SURVEY Appendix C.14
@@ -216,7 +220,7 @@ em_sell_kernel(const int32_t *__restrict__ queue, const int *__restrict__ qcount
                 const uint8_t *p = sideR + d.x;
                 const uint32_t ns = d.y;
                 if (!hazard) {
-#pragma unroll kSlotUnroll
+#pragma unroll U
                     for (uint32_t s = 0; s < ns; ++s, p += kSlotBytes) {
                         const double2 v = reinterpret_cast<const double2 *>(p)[lane];
                         const uint32_t oe = reinterpret_cast<const uint16_t *>(p + 512)[lane];

@@ -214,6 +214,81 @@ def quantdt_stage(args):
                     "counts by txid), median of 5; ms_host_packer = the same with csrc/quant_pack.cpp in front"}
 
 
+def _gen_table(args):
+    scale, s = args
+    from bambu_b200 import synthetic as S
+    ann = S.annotation_for("config4", SEED, scale)
+    return S.sample_arena(ann, s, d_rate=None, resample_frac=0.2, long_table=True)
+
+
+def _cpu_stage_one(tab):
+    """the per-sample quantification stage on one host core: host packer (csrc/quant_pack.cpp), the sparse oracle EM
+    (single thread), merge by txid -- what a BiocParallel worker does per sample, without CPM / rounding (which favours
+    the CPU arm)"""
+    import oracle
+    from bambu_b200 import quantify as Q
+    pk = Q.pack_quantDT_native(tab)
+    est = oracle.em_batched(pk.arena, mode=oracle.MODE_SPARSE, n_threads=1, **EM_PAR)[0]
+    q = Q.modifyQuantOut_removeDuplicates(pk, est)
+    out = np.full(int(q["txid"].max()), np.nan)
+    out[q["txid"] - 1] = q["uniqueCounts"]          # the unrounded assay: compared with the GPU's, double for double
+    return out
+
+
+def quant_stage_cohort(ctx, args):
+    """The whole quantification stage of a cohort from the long tables (what bambu() runs under bplapply, R/bambu.R:187-192,
+    after genEquiRCs): ONE call of bambu_quantDT_cohort -> the four n_tx x n_samples assays, tables in page-locked host
+    memory.  Beside it: the same stage per sample on the host cores (host packer + sparse oracle EM + host epilogue, one
+    sample per core, all cores), on a bounded number of samples."""
+    import torch
+    from bambu_b200 import quantify as Q
+    S_gpu = max(1, min(args.stage_samples, 100))
+    with mp.get_context("forkserver").Pool(max(1, min(S_gpu, os.cpu_count() or 8, 32))) as pool:
+        tables = pool.map(_gen_table, [(args.scale, s) for s in range(S_gpu)], chunksize=1)
+    n_tx = int(max(int(np.max(t["txid"])) for t in tables))
+    ann = np.arange(1, n_tx + 1, dtype=np.int64)
+    rows = int(sum(len(t["txid"]) for t in tables))
+    pinned = []
+    for t in tables:                      # page-locked copies of the table columns (what a caller would register once)
+        p = {}
+        for k, dt in (("GENEID", np.int64), ("txid", np.int64), ("eqClassId", np.int64), ("nobs", np.float64),
+                      ("equal", np.uint8), ("rcWidth", np.float64), ("txlen", np.float64)):
+            src = torch.from_numpy(np.ascontiguousarray(np.asarray(t[k]).astype(dt)))
+            dst = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+            dst.copy_(src)
+            p[k] = dst.numpy()
+        p["equal"] = p["equal"].view(np.bool_)
+        pinned.append(p)
+    inc = np.zeros(S_gpu)
+    Q.bambu_quantDT_cohort_native(pinned[:min(4, S_gpu)], ann, inc[:min(4, S_gpu)])           # warm-up: workspaces, plans
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        out = Q.bambu_quantDT_cohort_native(pinned, ann, inc)
+        ts.append(time.perf_counter() - t0)
+    gpu_s = min(ts)
+    res = {"samples": S_gpu, "table_rows": rows, "transcripts": n_tx, "ms": gpu_s * 1e3, "ms_per_sample": gpu_s * 1e3 / S_gpu,
+           "samples_per_sec": S_gpu / gpu_s, "h2d_bytes": rows * 49, "used_device": int(out["used_device"].sum()),
+           "what": "bambu_quantDT_cohort: long tables (page-locked host memory) -> GPU pack -> EM -> device epilogue -> "
+                   "4 assays n_tx x n_samples in host memory; best of 3"}
+    if not args.no_cpu:
+        import oracle
+        oracle.build()
+        cores = os.cpu_count() or 1
+        n_cpu = max(1, min(cores, S_gpu))
+        t0 = time.perf_counter()
+        with mp.get_context("forkserver").Pool(n_cpu) as pool:
+            cpu_counts = pool.map(_cpu_stage_one, tables[:n_cpu], chunksize=1)
+        cpu_s = time.perf_counter() - t0
+        same = all(np.array_equal(c, out["uniqueCounts"][:len(c), k], equal_nan=True) for k, c in enumerate(cpu_counts))
+        res["cpu"] = {"samples": n_cpu, "cores": cores, "seconds": cpu_s, "samples_per_sec": n_cpu / cpu_s,
+                      "uniqueCounts_identical_to_gpu": bool(same),
+                      "what": "per sample on one core: host packer + sparse oracle EM + host merge (no CPM / rounding); "
+                              "one sample per core, all cores at once (pool start-up included)"}
+        res["speedup_vs_cpu"] = res["samples_per_sec"] / res["cpu"]["samples_per_sec"]
+    return res
+
+
 def bind_to_gpu_numa_node(local):
     """Keep this rank's host threads -- and with them the first-touched pinned buffers -- on the CPUs next to its GPU
     (NVML's ideal affinity), so that eight ranks do not pull their arenas across the socket interconnect."""
@@ -340,6 +415,9 @@ class Slab:
         self.plan.run(**EM_PAR)
         self.est, self.iters, self.status = self.plan.download()
         _, nz_live = self.plan.download_live()
+        _, slots = self.plan.download_image_stats()
+        # SELL fill of the resident images: live entries over the 2 x 32 places of every slot, both sides together
+        self.sell_fill = float(2.0 * nz_live.sum() / max(64.0 * slots.sum(), 1.0))
         self.work = float((w.nnz_nonzero * self.iters).sum())              # nnz_g (aval != 0) x iters_g
         self.work_live = float((nz_live.astype(np.int64) * self.iters).sum())
         self.launches = self.plan.last_run_launches()
@@ -673,7 +751,10 @@ def run_b200(args):
             "work": {"nnz_iterations_per_step": work_all, "live_nnz_iterations_per_step": live_all,
                      "groups_per_gpu": slab.n_groups, "max_iters": int(slab.iters.max()),
                      "median_iters": float(np.median(slab.iters)), "last_step_ms": last, "gen_seconds": gen_s,
-                     "wire_seconds": slab.wire_s, "cpus_bound_to_gpu_numa_node": ctx.bound_cpus},
+                     "wire_seconds": slab.wire_s, "cpus_bound_to_gpu_numa_node": ctx.bound_cpus,
+                     "sell_fill": slab.sell_fill,
+                     "sell_fill_note": "live entries / places of the SELL slots (row + column side): what the padding to the "
+                                       "longest line of a 32-line slice costs (DESIGN.md 9)"},
         }
     parity_ok = True
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -716,6 +797,7 @@ def run_b200(args):
         if world == 1 and not args.no_stage:
             line["config2_single"] = config2_single(ctx, args)
             line["quantDT_stage"] = quantdt_stage(args)
+            line["quant_stage_cohort"] = quant_stage_cohort(ctx, args)
         print(json.dumps(line))
         if not parity_ok:
             raise SystemExit("bench: GPU results differ from the oracle on cohort sample 0 (see 'parity')")
@@ -735,6 +817,7 @@ def main():
     ap.add_argument("--cpu-frac", type=float, default=1.0, help="CPU arms run on 1/cpu-frac of one sample's groups")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stage", action="store_true", help="skip the quantDT_stage / config2_single latency measurements")
+    ap.add_argument("--stage-samples", type=int, default=32, help="samples of the quant_stage_cohort measurement")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling pass (N > 1)")
     ap.add_argument("--no-config3", action="store_true", help="skip the config-3 (giant loci) block")
     ap.add_argument("--config3-scale", type=float, default=float(os.environ.get("BAMBU_BENCH_CONFIG3_SCALE", "1.0")),

@@ -15,6 +15,15 @@ pytestmark = pytest.mark.gpu
 REL, ABS = 1e-6, 1e-9     # the tolerance north_star states
 
 
+@pytest.fixture(autouse=True, params=["latency", "throughput"])
+def kernel_mode(request, monkeypatch):
+    """Small arenas run on the latency instance of the EM kernel (256 threads, 4 slots in flight), big ones on the
+    throughput instances (64 / 128 threads): every test here runs on both."""
+    if request.param == "throughput":
+        monkeypatch.setenv("BAMBU_EM_LATENCY_GROUPS", "0")
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def em():
     from bambu_b200 import _lib

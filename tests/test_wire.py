@@ -96,6 +96,14 @@ def test_converter_rejects_malformed_arena():
 
 
 # ------------------------------------------------------------------------------------ GPU
+@pytest.fixture(autouse=True, params=["latency", "throughput"])
+def kernel_mode(request, monkeypatch):
+    """both instances of the EM kernel (see tests/test_em_gpu.py)"""
+    if request.param == "throughput":
+        monkeypatch.setenv("BAMBU_EM_LATENCY_GROUPS", "0")
+    return request.param
+
+
 def check_wire_against_oracle(oracle_mod, arena, **par):
     import bambu_b200.em as em
     from bambu_b200.wire import Wire
