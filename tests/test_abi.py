@@ -70,3 +70,25 @@ def test_synthetic_config2_shape():
     grp_of_row = np.repeat(np.arange(a.n_groups), M)
     col_global = a.grp_col_ptr[grp_of_row[rows_of]] + a.col_idx
     assert np.all(np.bincount(rows_of, weights=live[col_global], minlength=a.n_rows) > 0)
+
+
+def test_r_shim_typechecks(built_lib):
+    """r/b200_shim.c (the .Call binding a bambu maintainer would add) cannot be built here -- no R --
+    but it can be type-checked against include/bambu_em.h with stand-in R headers, and every library symbol it
+    calls must be exported."""
+    import shutil
+    import subprocess
+    shim = os.path.join(ROOT, "r", "b200_shim.c")
+    src = re.sub(r"/\*.*?\*/", "", open(shim).read(), flags=re.S)
+    used = set(re.findall(r"\b(bambu_(?:em|emWithL1|quant|wire)\w*)\s*\(", src))
+    assert {"bambu_em_batched", "bambu_emWithL1", "bambu_quantDT_dotC", "bambu_em_last_error", "bambu_em_shutdown"} <= used
+    L = built_lib.lib()
+    for n in used:
+        assert n in built_lib.SYMBOLS and hasattr(L, n), n
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-Wno-cast-function-type", "-fsyntax-only",
+                        "-I", os.path.join(ROOT, "tests", "r_stub"), "-I", os.path.join(ROOT, "include"), shim],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
