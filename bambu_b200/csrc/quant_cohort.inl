@@ -292,7 +292,7 @@ extern "C" int bambu_quantDT_cohort(int32_t n_samples, const int64_t *n_rows, co
     cudaGetDevice(&device);
     Args A = {n_samples, n_rows, gene_code, txid, eqClassId, nobs, equal, rcWidth, txlen, degradation_bias, maxiter, minvalue, conv,
               n_tx, annotation_txid, incompatible_total, sig_digit, assays, assays_device, d_rate, used_device};
-    int n_workers = 3;
+    int n_workers = 4;
     if (const char *e = getenv("BAMBU_COHORT_WORKERS")) n_workers = atoi(e);
     n_workers = std::max(1, std::min(std::min(n_workers, 8), std::max(n_samples, 1)));
     std::string first_error;

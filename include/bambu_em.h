@@ -267,7 +267,7 @@ void bambu_quantDT_dotC(const int *n_rows, const int *gene_code, const int *txid
  * modifyQuantOut, removeDuplicates, calculateCPM (denominator = sum(counts) + incompatible_total[s], R's long double
  * sum, result-row order), counts[match(annotation_txid, txid)], round(., sig_digit) of counts / CPM / fullLengthCounts
  * -- runs on the device and writes the sample's column of the four assays.  Samples are spread over a few worker
- * threads (BAMBU_COHORT_WORKERS, default 3) so that copies, packing and EM of different samples overlap.
+ * threads (BAMBU_COHORT_WORKERS, default 4) so that copies, packing and EM of different samples overlap.
  *
  *   assays         HOST, 4 * n_samples * n_tx doubles (may be NULL): assays[(k * n_samples + s) * n_tx + a], k = 0 counts,
  *                  1 CPM, 2 fullLengthCounts, 3 uniqueCounts -- i.e. four column-major n_tx x n_samples R matrices;

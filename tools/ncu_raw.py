@@ -8,7 +8,7 @@ want = ['Kernel Name', 'gpu__time_duration.sum', 'launch__grid_size', 'launch__b
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
         'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'smsp__warps_eligible.avg.per_cycle_active', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
-        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed', 'lts__t_bytes.sum',
         'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__thread_inst_executed_per_inst_executed.ratio',
         'sm__cycles_elapsed.max', 'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',

@@ -2,7 +2,7 @@
 
     # on the GPU box (one call; the plain run first, as the profiling recipe asks):
     python tools/slab_once.py 100 2 > gpurun_out/slab_plain.log 2>&1 && \
-    ncu --set full --clock-control none --import-source on -k regex:em_sell_kernel -s 6 -c 6 \
+    ncu --set full --clock-control none --import-source on -k regex:em_sell_kernel -s 9 -c 3 \
         -o gpurun_out/r2_em_sell_slab100 python tools/slab_once.py 100 2
     # here (no GPU needed):
     python tools/roofline_capture.py gpurun_out/r2_em_sell_slab100.ncu-rep 100
@@ -23,7 +23,7 @@ M = {
     "dram_read": "dram__bytes_read.sum",
     "dram_write": "dram__bytes_write.sum",
     "issue": "smsp__issue_active.avg.pct_of_peak_sustained_active",
-    "smem": "l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed",
+    "smem": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
     "smem_wavefronts": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
     "fp64": "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
     "dram": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -69,7 +69,7 @@ def main():
                 k[key] = None
                 continue
             v, u = num(r[col[name]]), units[col[name]]
-            if key in ("dram_read", "dram_write", "lts_bytes"):
+            if key in ("dram_read", "dram_write", "lts_bytes", "smem_dyn"):
                 v = to_bytes(v, u)
             elif key == "time_ns":
                 v = to_ns(v, u)
@@ -81,7 +81,7 @@ def main():
     commit = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
     res = {
         "capture": {"report": os.path.basename(rep), "samples": samples, "commit": commit,
-                    "command": "ncu --set full --clock-control none --import-source on -k regex:em_sell_kernel -s 6 -c 6 "
+                    "command": "ncu --set full --clock-control none --import-source on -k regex:em_sell_kernel -s 9 -c 3 "
                                f"python tools/slab_once.py {samples} 2",
                     "note": "durations under ncu are cold-cache and serialised: use the SHARES and the byte counts"},
         "kernels": [{"kernel": k["kernel"], "block": k["block"], "grid": k["grid"], "smem_dyn": k["smem_dyn"], "regs": k["regs"],

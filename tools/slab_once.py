@@ -12,19 +12,25 @@ import bench  # noqa: E402
 from bambu_b200.em import EmPlan  # noqa: E402
 from bambu_b200.wire import Wire  # noqa: E402
 
-samples = int(sys.argv[1]) if len(sys.argv) > 1 else 100
-runs = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-cache = f"/tmp/bambu_slab_{samples}.pkl"
-if os.path.exists(cache):
-    w = pickle.load(open(cache, "rb"))
-else:
-    w = Wire.from_arena(bench.make_cohort(range(samples)))
-    pickle.dump(w, open(cache, "wb"), protocol=4)
-with EmPlan(w) as plan:
-    plan.upload()
-    for _ in range(runs):
-        plan.run(**bench.EM_PAR)
-        plan.sync()
-    ms = plan.last_run_ms()
-    est, iters, status = plan.download()
-print(f"slab of {samples} samples: {w.n_groups} groups, last run {ms}, nnz-iterations {float((w.nnz_nonzero * iters).sum()):.4g}")
+def main():
+    samples = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+    runs = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    cache = f"/tmp/bambu_slab_{samples}.pkl"
+    if os.path.exists(cache):
+        w = pickle.load(open(cache, "rb"))
+    else:
+        w = Wire.from_arena(bench.make_cohort(range(samples)))
+        pickle.dump(w, open(cache, "wb"), protocol=4)
+    with EmPlan(w) as plan:
+        plan.upload()
+        for _ in range(runs):
+            plan.run(**bench.EM_PAR)
+            plan.sync()
+        ms = plan.last_run_ms()
+        est, iters, status = plan.download()
+    print(f"slab of {samples} samples: {w.n_groups} groups, last run {ms}, nnz-iterations {float((w.nnz_nonzero * iters).sum()):.4g}")
+
+
+
+if __name__ == "__main__":
+    main()
