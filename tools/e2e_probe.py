@@ -62,6 +62,10 @@ def main():
             print(f"    e2e per step: slowest rank {mx:.1f} ms, fastest {mn:.1f} ms", flush=True)
 
     run("rank 0 alone, default chunks", {"BAMBU_EM_CHUNK_MB": None}, solo=True)
+    if args.chunks:
+        for frac in ("1", "2", "3", "4", "1000"):
+            run(f"all ranks, chunks of at least 1/{frac} of the call", {"BAMBU_EM_CHUNK_MIN_FRACTION": frac})
+        os.environ.pop("BAMBU_EM_CHUNK_MIN_FRACTION", None)
     run("all ranks, default chunks (96 MB), tables into torch-pinned memory", {"BAMBU_EM_CHUNK_MB": None})
     if args.chunks:
         run("all ranks, 32 MB chunks", {"BAMBU_EM_CHUNK_MB": "32"})
