@@ -468,7 +468,10 @@ static int launch_pack(Slot &s, int bi, const SlotViews &v)
 static bool latency_mode(const Slot &s)
 {
     const char *e = getenv("BAMBU_EM_LATENCY_GROUPS");
-    return s.ng() <= (e ? atoll(e) : (int64_t)16384);
+    // measured on config-4 samples (3.6k groups each), device ms in latency / throughput mode: 1 sample 3.2 / 3.8,
+    // 2 samples 5.3 / 4.3, 4 samples 9.3 / 6.8, 13 samples 26.6 / 16.9 -- the latency instance only pays while the
+    // whole arena is resident at once
+    return s.ng() <= (e ? atoll(e) : (int64_t)6000);
 }
 
 static int launch_em(Slot &s, int c, const SlotViews &v)
