@@ -57,6 +57,7 @@ SYMBOLS = {
     "bambu_quant_merge": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, ctypes.POINTER(_i64)]),
     "bambu_quantDT": (ctypes.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _f64, _f64, _p, _p, _p, _p,
                                      ctypes.POINTER(_i64), ctypes.POINTER(_f64)]),
+    "bambu_quant_last_used_device": (ctypes.c_int, []),
     "bambu_quantDT_hostpack": (ctypes.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _f64, _f64, _p, _p, _p, _p,
                                               ctypes.POINTER(_i64), ctypes.POINTER(_f64)]),
     "bambu_quantDT_cohort": (ctypes.c_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _f64, _f64, _i64, _p, _p, _i32,

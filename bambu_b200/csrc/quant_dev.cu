@@ -521,12 +521,17 @@ inline int hostpack_any(int64_t n, const int *g, const int *t, const int *e, con
                                   minvalue, conv, txid_out, counts, full_length, unique_counts, n_result, d_rate);
 }
 
+// 1 when the last bambu_quantDT / bambu_quantDT_dotC call of this thread packed its table on the GPU, 0 when it went
+// through the host packer (a ~25x slower path: non-integer counts etc., see quant_dev.inl), -1 before any call
+static thread_local int g_last_used_device = -1;
+
 template <class IdT, class EqT>
 int quantdt_core(int64_t n, const IdT *gene_code, const IdT *txid, const IdT *eqClassId, const double *nobs,
                   const EqT *equal, const double *rcWidth, const double *txlen, int32_t degradation_bias,
                   int32_t maxiter, double minvalue, double conv, int64_t *txid_out, double *counts, double *full_length,
                   double *unique_counts, int64_t *n_result, double *d_rate_out)
 {
+    g_last_used_device = 0;
     const char *force_host = getenv("BAMBU_QUANT_HOST_PACK");
     if (force_host && force_host[0] == '1')
         return hostpack_any(n, gene_code, txid, eqClassId, nobs, equal, rcWidth, txlen, degradation_bias, maxiter,
@@ -584,6 +589,7 @@ int quantdt_core(int64_t n, const IdT *gene_code, const IdT *txid, const IdT *eq
         const auto t2 = now();
         rc = bambu_quant_merge(&P, est.data(), txid_out, counts, full_length, unique_counts, n_result);
         if (!rc && d_rate_out) *d_rate_out = P.d_rate;
+        if (!rc) g_last_used_device = 1;
         if (timing)
             fprintf(stderr, "[bambu_quantDT] rows %lld: H2D + device pack %.2f ms (%ld launches), EM %.2f ms, merge %.2f ms\n",
                     (long long)n, ms(t0, t1), x.launches, ms(t1, t2), ms(t2, now()));
@@ -681,6 +687,8 @@ int bambu_quantDT(int64_t n, const int64_t *gene_code, const int64_t *txid, cons
     return quantdt_core(n, gene_code, txid, eqClassId, nobs, equal, rcWidth, txlen, degradation_bias, maxiter, minvalue, conv,
                         txid_out, counts, full_length, unique_counts, n_result, d_rate_out);
 }
+
+int bambu_quant_last_used_device(void) { return g_last_used_device; }
 
 // bambu_quantDT for R's .C() interface, which needs no compiled shim: every argument is a pointer to one of R's
 // own vector types (integer = int, numeric = double, logical = int), scalars are length-1 vectors, the return code

@@ -373,7 +373,7 @@ def bambu_quantDT_native(readClassDt, emParameters=None, host_pack=False):
                         float(par["conv"]), ptr(t_out), ptr(c0), ptr(c1), ptr(c2), ctypes.byref(k), ctypes.byref(d)))
     m = int(k.value)
     return {"txid": t_out[:m], "counts": c0[:m], "fullLengthCounts": c1[:m], "uniqueCounts": c2[:m],
-            "d_rate": float(d.value)}
+            "d_rate": float(d.value), "used_device": (not host_pack) and bool(L.bambu_quant_last_used_device() == 1)}
 
 
 def bambu_quantDT_cohort_native(tables, annotation_txid, incompatible_totals=None, emParameters=None, sig_digit=5,

@@ -245,6 +245,9 @@ int bambu_quantDT(int64_t n_rows, const int64_t *gene_code, const int64_t *txid,
                   const double *nobs, const uint8_t *equal, const double *rcWidth, const double *txlen,
                   int32_t degradation_bias, int32_t maxiter, double minvalue, double conv, int64_t *txid_out,
                   double *counts, double *full_length, double *unique_counts, int64_t *n_result, double *d_rate);
+/* 1 if the last bambu_quantDT / bambu_quantDT_dotC call of this thread packed its table on the GPU, 0 if the table went
+ * through the host packer (same result, ~25x slower: see bambu_quantDT_hostpack), -1 before any call. */
+int bambu_quant_last_used_device(void);
 /* The same with the table packed by the host code of bambu_quant_pack_create (bambu_quantDT packs on the GPU and
  * uses this for tables its device formulation does not cover: non-integer or negative nobs, negative or
  * non-finite widths / lengths, a degradation rate that is not a finite number >= 0). */

@@ -346,3 +346,14 @@ def test_gpu_quantDT_with_giant_gene(built):
             total += n
     mass = got["counts"][np.isin(got["txid"], np.array(sorted(giant_tx)))].sum()
     assert np.isfinite(mass) and abs(mass - total) <= 1e-6 * total
+
+
+@pytest.mark.gpu
+def test_quantDT_reports_which_packer_ran(built):
+    """the host-packer path is a ~25x cliff: every entry point says which packer ran (bambu_quant_last_used_device)"""
+    rng = np.random.default_rng(5)
+    tab = random_long_table(rng, n_genes=50)
+    assert Q.bambu_quantDT_native(tab)["used_device"] is True
+    odd = dict(tab, nobs=[v + 0.5 if v else v for v in tab["nobs"]])
+    assert Q.bambu_quantDT_native(odd)["used_device"] is False
+    assert Q.bambu_quantDT_native(tab, host_pack=True)["used_device"] is False
