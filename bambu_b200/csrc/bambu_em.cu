@@ -134,7 +134,9 @@ struct Ctrl {   // device control block, zeroed at the start of every run
     unsigned long long pool_ctr;
     int qcount[8];
     int ticket[8];
-    unsigned int gflags[64 * 8]; // streamed tier, per team of CTAs: [0..7] hazard / stopping flags, [32..33] barrier
+    unsigned int gticket;        // streamed tier: next locus to hand to a team that has finished one
+    unsigned int gpad[3];
+    unsigned int gflags[64 * 16]; // streamed tier, per team of CTAs: [0..7] hazard / stopping flags, [32..33] barrier, [40] next locus
 };
 
 // ------------------------------------------------------------------------------
@@ -626,6 +628,10 @@ static int slot_prepare(Slot &s, const int64_t *grp_row_ptr, const int64_t *grp_
     s.giant_bytes = s.giant_bytes_prepared = goff;
     s.n_giant_prepared = s.n_giant;
     if (s.n_giant) {
+        if (const char *e = getenv("BAMBU_EM_GIANT_SORT")) {       // experiments: 1 = largest first, 2 = smallest first
+            if (e[0] == '1') std::stable_sort(giants.begin(), giants.end(), [&](const GiantDesc &a, const GiantDesc &b) { return s.hE[a.g - g0] > s.hE[b.g - g0]; });
+            if (e[0] == '2') std::stable_sort(giants.begin(), giants.end(), [&](const GiantDesc &a, const GiantDesc &b) { return s.hE[a.g - g0] < s.hE[b.g - g0]; });
+        }
         TRY(s.h_gdesc.ensure(sizeof(GiantDesc) * giants.size()));
         memcpy(s.h_gdesc.p, giants.data(), sizeof(GiantDesc) * giants.size());
         TRY(s.gdesc.ensure(sizeof(GiantDesc) * giants.size(), &s.device_bytes));
@@ -794,12 +800,18 @@ static int launch_giant_em(Slot &s, const SlotViews &v, int first, int count, cu
     double *est = v.est;
     int32_t *iters = v.iters, *status = v.status;
     unsigned int *gflags = v.ctrl->gflags;
-    // loci are iterated by teams of CTAs (giant.cuh); more teams = more overlap, fewer warps per locus
+    unsigned int *gticket = &v.ctrl->gticket;
+    // Loci are iterated by teams of CTAs (giant.cuh): an update of one locus is bound by barrier round trips and add
+    // chains, not by bandwidth, so several loci in flight fill the GPU better.  Measured on config 3 (50 loci of 2-3 M
+    // entries): 1 team 421 ms, 2: 288, 4: 250-278, 8: 249, 10: 234-242, 12: 241, 16: 240-246; on a 6-locus shard:
+    // 2 teams 35.0, 4: 39-41, 6 and more: 30.5 ms.  A team that finishes a locus takes the next one from a ticket
+    // (iteration counts -- 300 to 1600 updates per locus -- are not known in advance, so no static split is safe;
+    // sorting the loci by size in either direction changed nothing).
     int n_teams = 1;
     if (const char *e = getenv("BAMBU_EM_GIANT_TEAMS")) n_teams = atoi(e);
-    else n_teams = (n_giant >= 8) ? 4 : (n_giant >= 2 ? 2 : 1);
-    n_teams = std::max(1, std::min(std::min(n_teams, 8), n_giant));
-    void *args[] = {&descs, &n_giant, &gbuf_c, &gbuf, &grp, &rows, &P, &est, &iters, &status, &gflags, &n_teams};
+    else n_teams = 10;
+    n_teams = std::max(1, std::min(std::min(n_teams, 16), n_giant));
+    void *args[] = {&descs, &n_giant, &gbuf_c, &gbuf, &grp, &rows, &P, &est, &iters, &status, &gflags, &n_teams, &gticket};
     // dynamic shared memory: one private copy of theta per CTA + the per-warp staging
     const size_t smem = std::max<size_t>(s.giant_smem, 1024);
     int per_sm = 0;

@@ -413,12 +413,13 @@ __global__ void __launch_bounds__(T)
 em_giant_kernel(const GiantDesc *__restrict__ descs, int n_giant, const uint8_t *gbuf_c, uint8_t *gbuf,
                 const int64_t *__restrict__ grp_row_ptr, int64_t total_rows, EmParams P, double *__restrict__ est,
                 int32_t *__restrict__ iters, int32_t *__restrict__ status, unsigned int *gflags /* zeroed */,
-                int n_teams)
+                int n_teams, unsigned int *ticket /* zeroed */)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     // The grid is split into n_teams teams of CTAs; a team iterates on one locus at a time with its
     // own barrier, so the barrier / latency-bound stretches of one locus overlap with the work of the
-    // others.  Team t owns CTAs {t, t + n_teams, ...} and loci {t, t + n_teams, ...}.
+    // others.  Team t owns CTAs {t, t + n_teams, ...}; it starts on locus t and then takes whatever locus the ticket
+    // hands out next.
     const int team = blockIdx.x % n_teams, team_rank = blockIdx.x / n_teams;
     const unsigned int n_ctas = (gridDim.x - team + n_teams - 1) / n_teams;      // CTAs of this team
     unsigned int *tflags = gflags + 64 * team;      // per team: [0..7] flags, [32..33] barrier (own cache line)
@@ -432,7 +433,7 @@ em_giant_kernel(const GiantDesc *__restrict__ descs, int n_giant, const uint8_t 
     const int64_t gwarp = (int64_t)(tid >> 5) * n_ctas + team_rank;
     (void)gbuf_c;
 
-    for (int gi = team; gi < n_giant; gi += n_teams) {
+    for (int gi = team; gi < n_giant;) {
         const GiantDesc D = descs[gi];
         const int M = D.M, NL = D.NL;
         uint8_t *img = gbuf + D.base;
@@ -625,8 +626,10 @@ em_giant_kernel(const GiantDesc *__restrict__ descs, int n_giant, const uint8_t 
             iters[D.g] = iter;
             status[D.g] = ((iter >= P.maxiter - 1 && over) ? 1 : 0) | (__ldcg(&hz[3]) ? 2 : 0);
             hz[3] = 0;
+            tflags[40] = (unsigned int)n_teams + atomicAdd(ticket, 1u);      // this team's next locus
         }
         grid_barrier(bar, n_ctas);
+        gi = (int)__ldcg(&tflags[40]);
     }
 }
 
