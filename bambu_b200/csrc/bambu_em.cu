@@ -558,7 +558,7 @@ static int slot_prepare(Slot &s, const int64_t *grp_row_ptr, const int64_t *grp_
         const double ub = 20.0 * (double)e + 18.0 * (double)(M + N) + 64.0;
         if (M > kMaxIndex || N > kMaxIndex || M + N > kMaxVecElems || ub > (double)kSmemMax || forced_giant) {
             // streamed tier: image in global memory, all SMs iterate on this one group
-            if (8 * (M + 1) + 16 + 512 * (kGiantThreads / 32) > (int64_t)kSmemMax || M > INT32_MAX / 8 || N > INT32_MAX / 2 || e > (int64_t)UINT32_MAX - 64)
+            if (8 * (M + 1) + 16 + (int64_t)giant_stage_bytes(1) * (kGiantThreads / 32) > (int64_t)kSmemMax || M > INT32_MAX / 8 || N > INT32_MAX / 2 || e > (int64_t)UINT32_MAX - 64)
                 return fail(BAMBU_EM_EINVAL, "group %lld (M=%lld N=%lld entries=%lld) exceeds the streamed tier",
                             (long long)g, (long long)M, (long long)N, (long long)e);
             GiantDesc d;
@@ -568,7 +568,7 @@ static int slot_prepare(Slot &s, const int64_t *grp_row_ptr, const int64_t *grp_
             d.base = goff;
             goff += d.total;
             giants.push_back(d);
-            gsmem = std::max<uint32_t>(gsmem, (uint32_t)(8 * (M + 1) + 16 + 512 * (kGiantThreads / 32)));
+            gsmem = std::max<uint32_t>(gsmem, (uint32_t)(8 * (M + 1) + 16));      // theta of the widest locus; staging is added at launch
             continue;
         }
         const uint32_t bytes = em_smem_bytes((uint32_t)M, (uint32_t)N, (uint32_t)e);
@@ -811,9 +811,16 @@ static int launch_giant_em(Slot &s, const SlotViews &v, int first, int count, cu
     if (const char *e = getenv("BAMBU_EM_GIANT_TEAMS")) n_teams = atoi(e);
     else n_teams = 10;
     n_teams = std::max(1, std::min(std::min(n_teams, 16), n_giant));
-    void *args[] = {&descs, &n_giant, &gbuf_c, &gbuf, &grp, &rows, &P, &est, &iters, &status, &gflags, &n_teams, &gticket};
+    // rows per warp block in the M-phase (giant.cuh).  Config 3, 10 teams: rb 1: 264 ms, 2: 221, 4: 221, 8: 233 (too few
+    // blocks for the warps of a team).  At 221 ms the tier streams 24 B x 51.3 G nnz-iterations = 1.23 TB in 0.221 s =
+    // 5.6 TB/s: 0.85 of the measured HBM copy peak -- ten loci of ~100 MB each do not fit the L2, so every update
+    // re-reads its locus from HBM and the add chains are no longer what bounds it.
+    int rb = 4;
+    if (const char *e = getenv("BAMBU_EM_GIANT_RB")) rb = std::max(1, std::min(8, atoi(e)));
+    while (rb > 1 && (size_t)s.giant_smem + (size_t)giant_stage_bytes(rb) * (kGiantThreads / 32) > (size_t)kSmemMax) rb /= 2;
+    void *args[] = {&descs, &n_giant, &gbuf_c, &gbuf, &grp, &rows, &P, &est, &iters, &status, &gflags, &n_teams, &gticket, &rb};
     // dynamic shared memory: one private copy of theta per CTA + the per-warp staging
-    const size_t smem = std::max<size_t>(s.giant_smem, 1024);
+    const size_t smem = std::max<size_t>((size_t)s.giant_smem + (size_t)giant_stage_bytes(rb) * (kGiantThreads / 32), 1024);
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_giant_kernel<kGiantThreads>, kGiantThreads, smem));
     if (per_sm < 1) return fail(BAMBU_EM_ECUDA, "streamed EM kernel does not fit an SM");
@@ -910,7 +917,7 @@ static int slot_spill_to_streamed(Slot &s)
     for (size_t k = 0; k < ng; ++k) {
         if (gi[k].cls != -1) continue;
         const int64_t M = s.hM[k], N = s.hN[k], e = s.hE[k];
-        if (8 * (M + 1) + 16 + 512 * (kGiantThreads / 32) > (int64_t)kSmemMax)
+        if (8 * (M + 1) + 16 + (int64_t)giant_stage_bytes(1) * (kGiantThreads / 32) > (int64_t)kSmemMax)
             return fail(BAMBU_EM_EINVAL, "group %lld (M=%lld) exceeds the streamed tier", (long long)(s.g0 + (int64_t)k), (long long)M);
         GiantDesc d;
         memset(&d, 0, sizeof d);
@@ -919,7 +926,7 @@ static int slot_spill_to_streamed(Slot &s)
         d.base = s.giant_bytes;
         s.giant_bytes += d.total;
         s.giants.push_back(d);
-        s.giant_smem = std::max<uint32_t>(s.giant_smem, (uint32_t)(8 * (M + 1) + 16 + 512 * (kGiantThreads / 32)));
+        s.giant_smem = std::max<uint32_t>(s.giant_smem, (uint32_t)(8 * (M + 1) + 16));
     }
     const int count = (int)s.giants.size() - first;
     if (count == 0) return fail(BAMBU_EM_ECUDA, "device reported an oversized group but none is marked");

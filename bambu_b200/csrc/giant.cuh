@@ -408,12 +408,64 @@ __device__ __forceinline__ void row_streams(const uint32_t *__restrict__ cidx, c
     sB = __shfl_sync(0xffffffffu, acc, 1);
 }
 
+// ---- M-phase of a block of `rb` rows by one warp ------------------------------------------------------------------
+// An ordered sum is a chain of dependent FP64 adds (8.4 cycles each): one row per warp keeps 2 of 32 lanes adding.  Here
+// a warp owns rb rows = 2*rb parity streams (segments): for every batch of 32 entries the whole warp forms the products
+// of each segment in turn (coalesced value / index loads, one ratio gather per lane) and parks them in shared memory;
+// then lane s adds the 32 products of segment s in index order -- 2*rb chains advance per instruction instead of 2.
+// Same terms, same order per stream as row_streams / em_sell.cuh: identical doubles.
+constexpr int kStageStride = 33;                 // doubles per segment in the staging area (33: conflict-free for the adding lanes)
+__host__ __device__ inline uint32_t giant_stage_bytes(int rb) { return (uint32_t)(2 * rb * kStageStride * 8); }
+
+template <bool HAZARD>
+__device__ __forceinline__ double row_block_streams(const uint32_t *__restrict__ hp, const uint32_t *__restrict__ cidx,
+                                                    const double *__restrict__ cval, int r0, int nr, int lane,
+                                                    const double *theta, const double *ratio, double *stage)
+{
+    const int nseg = 2 * nr;
+    // the lane's own segment in the add stage
+    uint32_t my_lo = 0, my_n = 0;
+    if (lane < nseg) { my_lo = hp[2 * r0 + lane]; my_n = hp[2 * r0 + lane + 1] - my_lo; }
+    uint32_t nmax = my_n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+    double acc = 0.0;
+    for (uint32_t base = 0; base < nmax; base += 32) {
+#pragma unroll 4
+        for (int seg = 0; seg < nseg; ++seg) {
+            const uint32_t lo = __shfl_sync(0xffffffffu, my_lo, seg);           // warp-uniform: lane `seg` holds the bounds
+            const uint32_t hi = lo + __shfl_sync(0xffffffffu, my_n, seg);
+            const uint32_t k = lo + base + lane;
+            double t = 0.0;
+            if (k < hi) {
+                const double th = theta[r0 + (seg >> 1)];
+                t = __dmul_rn(__dmul_rn(cval[k], th), __ldcg(ratio + cidx[k]));
+                if (HAZARD) { if (t != t) t = 0.0; }          // replace(nan, 0)  (src/em.cpp:49)
+            }
+            stage[seg * kStageStride + lane] = t;
+        }
+        __syncwarp();
+        if (lane < nseg && base < my_n) {
+            const double *src = stage + lane * kStageStride;
+            const int n = (int)min(32u, my_n - base);
+            if (n == 32) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) acc = __dadd_rn(acc, src[q]);
+            } else {
+                for (int q = 0; q < n; ++q) acc = __dadd_rn(acc, src[q]);
+            }
+        }
+        __syncwarp();
+    }
+    return acc;      // lane 2r: even-column stream of row r0 + r, lane 2r + 1: odd-column stream
+}
+
 template <int T>
 __global__ void __launch_bounds__(T)
 em_giant_kernel(const GiantDesc *__restrict__ descs, int n_giant, const uint8_t *gbuf_c, uint8_t *gbuf,
                 const int64_t *__restrict__ grp_row_ptr, int64_t total_rows, EmParams P, double *__restrict__ est,
                 int32_t *__restrict__ iters, int32_t *__restrict__ status, unsigned int *gflags /* zeroed */,
-                int n_teams, unsigned int *ticket /* zeroed */)
+                int n_teams, unsigned int *ticket /* zeroed */, int rb /* rows per warp block: 1, 2, 4 or 8 */)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     // The grid is split into n_teams teams of CTAs; a team iterates on one locus at a time with its
@@ -460,8 +512,8 @@ em_giant_kernel(const GiantDesc *__restrict__ descs, int n_giant, const uint8_t 
         // [4..5] "delta > conv" by update parity, [6..7] non-finite theta count by update parity
         unsigned int *hz = tflags;
         const int64_t row0 = grp_row_ptr[D.g];
-        // per-warp staging of 2 x 32 products behind theta[M+1]
-        double *stage = reinterpret_cast<double *>(smem + align_up(8u * (uint32_t)(M + 1), 16)) + 64 * (tid >> 5);
+        // per-warp staging of the products of 2 * rb segments behind theta[M+1]
+        double *stage = reinterpret_cast<double *>(smem + align_up(8u * (uint32_t)(M + 1), 16) + giant_stage_bytes(rb) * (uint32_t)(tid >> 5));
 
         for (int i = tid; i < M; i += T) theta[i] = 1.0;   // src/em.cpp:20-21
         if (tid == 0) theta[M] = 0.0;                       // padding entries of the column SELL point here
@@ -513,23 +565,22 @@ em_giant_kernel(const GiantDesc *__restrict__ descs, int n_giant, const uint8_t 
             const bool hazard = (__ldcg(&hz[par]) != 0) || (nP != 0);
             // every CTA is past the barrier, so nobody still reads the other parity's flags
             if (gtid == 0) { hz[par ^ 1] = 0; hz[4 + (par ^ 1)] = 0; hz[6 + (par ^ 1)] = 0; }
-            for (int64_t i = gwarp; i < M; i += gwarps) {
-                const double th = theta[i];
-                const uint32_t loA = hp[2 * i], hiA = hp[2 * i + 1], hiB = hp[2 * i + 2];
-                double sA, sB;
-                if (hazard) row_streams<true>(cidx, cval, loA, hiA, hiA, hiB, lane, th, ratio, stage, sA, sB);
-                else row_streams<false>(cidx, cval, loA, hiA, hiA, hiB, lane, th, ratio, stage, sA, sB);
-                const double after = div_small_numerator(__dadd_rn(sA, sB), rs[i]);     // == __ddiv_rn; every lane: same value
-                bool inband = false;
-                double diff = 0.0;
-                int flag = (P.conv < 0.0) ? 1 : 0;
-                if (after > P.minvalue) {
-                    diff = fabs(__dadd_rn(after, -th));
-                    if (diff > __dmul_rn(after, P.conv_hi)) flag = 1;
-                    else inband = (diff >= __dmul_rn(after, P.conv_lo));
-                }
-                if (inband && __ddiv_rn(diff, after) > P.conv) flag = 1;   // warp-uniform: all lanes agree
-                if (lane == 0) {
+            const int64_t nBlocks = ((int64_t)M + rb - 1) / rb;
+            for (int64_t blk = gwarp; blk < nBlocks; blk += gwarps) {
+                const int r0 = (int)blk * rb, nr = min(rb, M - r0);
+                const double acc = hazard ? row_block_streams<true>(hp, cidx, cval, r0, nr, lane, theta, ratio, stage)
+                                          : row_block_streams<false>(hp, cidx, cval, r0, nr, lane, theta, ratio, stage);
+                const double other = __shfl_down_sync(0xffffffffu, acc, 1);
+                if (lane < 2 * nr && !(lane & 1)) {          // lane 2r forms theta' of row r0 + r and its share of the stopping test
+                    const int i = r0 + (lane >> 1);
+                    const double th = theta[i];
+                    const double after = div_small_numerator(__dadd_rn(acc, other), rs[i]);     // == __ddiv_rn
+                    int flag = (P.conv < 0.0) ? 1 : 0;
+                    if (after > P.minvalue) {
+                        const double diff = fabs(__dadd_rn(after, -th));
+                        if (diff > __dmul_rn(after, P.conv_hi)) flag = 1;
+                        else if (diff >= __dmul_rn(after, P.conv_lo) && __ddiv_rn(diff, after) > P.conv) flag = 1;
+                    }
                     S[i] = after;
                     if (flag) atomicOr(&hz[4 + par], 1u);
                     if (!is_finite(after)) atomicAdd(&hz[6 + par], 1u);

@@ -15,10 +15,10 @@ def main():
     shard = S.config3_arena(1.0, loci=[3, 11, 19, 27, 35, 43], small=False, workers=6, mp_context="forkserver")
     for name, arena in (("50 loci", full), ("6 loci", shard)):
         w = Wire.from_arena(arena)
-        for teams, srt in (("8", "0"), ("8", "1"), ("8", "2"), ("10", "0"), ("10", "2"), ("12", "0"), ("16", "0")):
+        for teams, srt in (("10", "rb8"), ("10", "rb4"), ("10", "rb2"), ("10", "rb1"), ("6", "rb8"), ("16", "rb8"), ("4", "rb8")):
             os.environ["BAMBU_EM_GIANT_TEAMS"] = teams
-            os.environ["BAMBU_EM_GIANT_SORT"] = srt
-            teams = teams + "/sort" + srt
+            os.environ["BAMBU_EM_GIANT_RB"] = srt[2:]
+            teams = teams + "/" + srt
             with EmPlan(w) as plan:
                 plan.upload()
                 ms = []
