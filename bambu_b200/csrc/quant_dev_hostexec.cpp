@@ -25,6 +25,7 @@ inline void qd_min(uint64_t *p, uint64_t v) { if (v < *p) *p = v; }
 inline void qd_max(uint64_t *p, uint64_t v) { if (v > *p) *p = v; }
 
 #include "quant_dev.inl"
+#include "r_round.h"
 
 namespace {
 
@@ -137,6 +138,11 @@ double qd_hostexec_ext_sum(const double *x, int64_t n)
     bool oor = false;
     const double d = qd::ext_to_double(acc, &oor);
     return oor ? NAN : d;
+}
+// R's round(x, digits) as the device epilogue of the cohort stage does it (r_round.h)
+void qd_hostexec_r_round(const double *x, int64_t n, int digits, double *out)
+{
+    for (int64_t i = 0; i < n; ++i) out[i] = qd::r_round(x[i], digits);
 }
 double qd_hostexec_ld_sum(const double *x, int64_t n)
 {

@@ -72,6 +72,23 @@ def hostexec_pack(L, tab, bias):
     return out
 
 
+def test_r_round_matches_the_host_mirror(hx):
+    """csrc/r_round.h (what the device epilogue of bambu_quantDT_cohort rounds with) == assays.r_round (the mirror of
+    R's round() that is pinned on the reference's stored assays), incl. exact binary ties, tiny and huge values."""
+    from bambu_b200.assays import r_round
+    hx.qd_hostexec_r_round.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]
+    hx.qd_hostexec_r_round.restype = None
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(0, 1e6, 60000), rng.uniform(0, 1, 30000) * 10.0 ** rng.integers(-12, 3, 30000),
+                        np.round(rng.uniform(0, 100, 20000), 5) + 0.000005, (rng.integers(0, 10 ** 8, 20000) * 2 + 1) / 2e5,
+                        np.array([0.0, -0.0, 2.5e-6, 1.5e-5, 0.5, 2.5, 1e300, 5e-324, 1e-20, 123456789.123455, 0.000005, 0.000015,
+                                  0.000025, -3.141592653589793, 4.4093676540475e-07, np.nan, np.inf, -np.inf, 2.0 ** 53, 1e11 + 0.5])])
+    for digits in (5, 0, 2, 8):
+        out = np.zeros_like(x)
+        hx.qd_hostexec_r_round(x.ctypes.data_as(ctypes.c_void_p), len(x), digits, out.ctypes.data_as(ctypes.c_void_p))
+        assert_same_doubles(out, r_round(x, digits), f"round(x, {digits})")
+
+
 def test_integer_x87_sum(hx):
     """ext_add / ext_to_double == `long double s; s += x; (double)s` (what R's sum() does on x86-64)."""
     rng = np.random.default_rng(5)
