@@ -809,14 +809,13 @@ static int launch_giant_em(Slot &s, const SlotViews &v, int first, int count, cu
     // sorting the loci by size in either direction changed nothing).
     int n_teams = 1;
     if (const char *e = getenv("BAMBU_EM_GIANT_TEAMS")) n_teams = atoi(e);
-    else n_teams = 10;
+    else n_teams = 12;
     n_teams = std::max(1, std::min(std::min(n_teams, 16), n_giant));
-    // rows per warp block in the M-phase (giant.cuh).  Config 3, 10 teams: rb 1: 264 ms, 2: 221, 4: 221, 8: 233 (too few
-    // blocks for the warps of a team).  At 221 ms the tier streams 24 B x 51.3 G nnz-iterations = 1.23 TB in 0.221 s =
-    // 5.6 TB/s: 0.85 of the measured HBM copy peak -- ten loci of ~100 MB each do not fit the L2, so every update
-    // re-reads its locus from HBM and the add chains are no longer what bounds it.
-    int rb = 4;
-    if (const char *e = getenv("BAMBU_EM_GIANT_RB")) rb = std::max(1, std::min(8, atoi(e)));
+    // rows per warp block in the M-phase (giant.cuh): 2 rows = 4 parity streams per warp, the loads of the next batch in
+    // flight while the current one is multiplied and added.  Config 3 (50 loci): one row per warp 238 ms (round-1 code,
+    // 10 teams), blocks of 2 / 4 / 8 rows without the prefetch 221 / 221 / 233, 2 rows with it 203 (10 teams), 199 (12).
+    int rb = 2;
+    if (const char *e = getenv("BAMBU_EM_GIANT_RB")) rb = atoi(e) >= 2 ? 2 : 1;
     while (rb > 1 && (size_t)s.giant_smem + (size_t)giant_stage_bytes(rb) * (kGiantThreads / 32) > (size_t)kSmemMax) rb /= 2;
     void *args[] = {&descs, &n_giant, &gbuf_c, &gbuf, &grp, &rows, &P, &est, &iters, &status, &gflags, &n_teams, &gticket, &rb};
     // dynamic shared memory: one private copy of theta per CTA + the per-warp staging

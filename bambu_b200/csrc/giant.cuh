@@ -417,31 +417,57 @@ __device__ __forceinline__ void row_streams(const uint32_t *__restrict__ cidx, c
 constexpr int kStageStride = 33;                 // doubles per segment in the staging area (33: conflict-free for the adding lanes)
 __host__ __device__ inline uint32_t giant_stage_bytes(int rb) { return (uint32_t)(2 * rb * kStageStride * 8); }
 
-template <bool HAZARD>
+template <bool HAZARD, int NSEG>
 __device__ __forceinline__ double row_block_streams(const uint32_t *__restrict__ hp, const uint32_t *__restrict__ cidx,
                                                     const double *__restrict__ cval, int r0, int nr, int lane,
                                                     const double *theta, const double *ratio, double *stage)
 {
-    const int nseg = 2 * nr;
+    const int nseg = 2 * nr;          // <= NSEG
     // the lane's own segment in the add stage
     uint32_t my_lo = 0, my_n = 0;
     if (lane < nseg) { my_lo = hp[2 * r0 + lane]; my_n = hp[2 * r0 + lane + 1] - my_lo; }
     uint32_t nmax = my_n;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+    // per segment (warp-uniform): bounds and the row's theta; lane `seg` holds the bounds
+    uint32_t lo[NSEG], hi[NSEG];
+    double th[NSEG];
+#pragma unroll
+    for (int seg = 0; seg < NSEG; ++seg) {
+        lo[seg] = __shfl_sync(0xffffffffu, my_lo, seg);
+        hi[seg] = lo[seg] + __shfl_sync(0xffffffffu, my_n, seg);
+        th[seg] = (seg < nseg) ? theta[r0 + (seg >> 1)] : 0.0;
+    }
+    // software pipeline: the values / column indices of batch b + 1 are in flight while batch b gathers its ratios,
+    // multiplies and adds (the SM issues in order: a load must be issued well before its first use)
+    double v[NSEG];
+    uint32_t c[NSEG];
+#pragma unroll
+    for (int seg = 0; seg < NSEG; ++seg) {
+        const uint32_t k = lo[seg] + lane;
+        const bool in = k < hi[seg];
+        v[seg] = in ? cval[k] : 0.0;
+        c[seg] = in ? cidx[k] : 0xffffffffu;
+    }
     double acc = 0.0;
     for (uint32_t base = 0; base < nmax; base += 32) {
-#pragma unroll 4
-        for (int seg = 0; seg < nseg; ++seg) {
-            const uint32_t lo = __shfl_sync(0xffffffffu, my_lo, seg);           // warp-uniform: lane `seg` holds the bounds
-            const uint32_t hi = lo + __shfl_sync(0xffffffffu, my_n, seg);
-            const uint32_t k = lo + base + lane;
-            double t = 0.0;
-            if (k < hi) {
-                const double th = theta[r0 + (seg >> 1)];
-                t = __dmul_rn(__dmul_rn(cval[k], th), __ldcg(ratio + cidx[k]));
-                if (HAZARD) { if (t != t) t = 0.0; }          // replace(nan, 0)  (src/em.cpp:49)
-            }
+        double vn[NSEG];
+        uint32_t cn[NSEG];
+#pragma unroll
+        for (int seg = 0; seg < NSEG; ++seg) {            // batch b + 1
+            const uint32_t k = lo[seg] + base + 32 + lane;
+            const bool in = k < hi[seg];
+            vn[seg] = in ? cval[k] : 0.0;
+            cn[seg] = in ? cidx[k] : 0xffffffffu;
+        }
+        double r[NSEG];
+#pragma unroll
+        for (int seg = 0; seg < NSEG; ++seg) r[seg] = (c[seg] != 0xffffffffu) ? __ldcg(ratio + c[seg]) : 0.0;
+#pragma unroll
+        for (int seg = 0; seg < NSEG; ++seg) {
+            double t = __dmul_rn(__dmul_rn(v[seg], th[seg]), r[seg]);
+            if (HAZARD) { if (t != t) t = 0.0; }          // replace(nan, 0)  (src/em.cpp:49); absent entries are 0 * th * 0
+            if (c[seg] == 0xffffffffu) t = 0.0;
             stage[seg * kStageStride + lane] = t;
         }
         __syncwarp();
@@ -456,8 +482,19 @@ __device__ __forceinline__ double row_block_streams(const uint32_t *__restrict__
             }
         }
         __syncwarp();
+#pragma unroll
+        for (int seg = 0; seg < NSEG; ++seg) { v[seg] = vn[seg]; c[seg] = cn[seg]; }
     }
     return acc;      // lane 2r: even-column stream of row r0 + r, lane 2r + 1: odd-column stream
+}
+
+template <bool HAZARD>
+__device__ __forceinline__ double row_block_dispatch(int rb, const uint32_t *__restrict__ hp, const uint32_t *__restrict__ cidx,
+                                                     const double *__restrict__ cval, int r0, int nr, int lane,
+                                                     const double *theta, const double *ratio, double *stage)
+{
+    if (rb == 1) return row_block_streams<HAZARD, 2>(hp, cidx, cval, r0, nr, lane, theta, ratio, stage);
+    return row_block_streams<HAZARD, 4>(hp, cidx, cval, r0, nr, lane, theta, ratio, stage);      // rb == 2
 }
 
 template <int T>
@@ -465,7 +502,7 @@ __global__ void __launch_bounds__(T)
 em_giant_kernel(const GiantDesc *__restrict__ descs, int n_giant, const uint8_t *gbuf_c, uint8_t *gbuf,
                 const int64_t *__restrict__ grp_row_ptr, int64_t total_rows, EmParams P, double *__restrict__ est,
                 int32_t *__restrict__ iters, int32_t *__restrict__ status, unsigned int *gflags /* zeroed */,
-                int n_teams, unsigned int *ticket /* zeroed */, int rb /* rows per warp block: 1, 2, 4 or 8 */)
+                int n_teams, unsigned int *ticket /* zeroed */, int rb /* rows per warp block: 1 or 2 */)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     // The grid is split into n_teams teams of CTAs; a team iterates on one locus at a time with its
@@ -568,8 +605,8 @@ em_giant_kernel(const GiantDesc *__restrict__ descs, int n_giant, const uint8_t 
             const int64_t nBlocks = ((int64_t)M + rb - 1) / rb;
             for (int64_t blk = gwarp; blk < nBlocks; blk += gwarps) {
                 const int r0 = (int)blk * rb, nr = min(rb, M - r0);
-                const double acc = hazard ? row_block_streams<true>(hp, cidx, cval, r0, nr, lane, theta, ratio, stage)
-                                          : row_block_streams<false>(hp, cidx, cval, r0, nr, lane, theta, ratio, stage);
+                const double acc = hazard ? row_block_dispatch<true>(rb, hp, cidx, cval, r0, nr, lane, theta, ratio, stage)
+                                          : row_block_dispatch<false>(rb, hp, cidx, cval, r0, nr, lane, theta, ratio, stage);
                 const double other = __shfl_down_sync(0xffffffffu, acc, 1);
                 if (lane < 2 * nr && !(lane & 1)) {          // lane 2r forms theta' of row r0 + r and its share of the stopping test
                     const int i = r0 + (lane >> 1);
