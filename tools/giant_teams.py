@@ -15,7 +15,7 @@ def main():
     shard = S.config3_arena(1.0, loci=[3, 11, 19, 27, 35, 43], small=False, workers=6, mp_context="forkserver")
     for name, arena in (("50 loci", full), ("6 loci", shard)):
         w = Wire.from_arena(arena)
-        for teams, srt in (("10", "rb2"), ("10", "rb1"), ("8", "rb2"), ("12", "rb2"), ("16", "rb2")):
+        for teams, srt in (("12", "rb2"), ("12", "rb1"), ("10", "rb2")):
             os.environ["BAMBU_EM_GIANT_TEAMS"] = teams
             os.environ["BAMBU_EM_GIANT_RB"] = srt[2:]
             teams = teams + "/" + srt
