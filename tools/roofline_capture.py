@@ -46,7 +46,7 @@ def num(x):
 
 def to_bytes(v, unit):
     k = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
-    return None if v is None else v * k.get(unit, 1)
+    return None if v is None else v * k.get(unit.split("/")[0], 1)
 
 
 def to_ns(v, unit):
