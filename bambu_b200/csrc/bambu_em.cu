@@ -750,7 +750,7 @@ static int slot_upload_v2(Slot &s, const WireHost &h)
 // ---- streamed tier launches over descs [first, first + count) ---------------------------------
 static int launch_giant_pack(Slot &s, const SlotViews &v, int first, int count, cudaStream_t st)
 {
-    if (s.v2 && !getenv("BAMBU_EM_GIANT_PACK_1CTA")) {
+    if (s.v2) {
         // wire form v2: every phase is a flat grid over (locus, tile) -- the whole GPU packs (giant_pack.cuh)
         GiantDesc *d = s.gdesc.as<GiantDesc>() + first;
         uint8_t *gb = s.gbuf.as<uint8_t>();
@@ -775,12 +775,8 @@ static int launch_giant_pack(Slot &s, const SlotViews &v, int first, int count, 
         s.launches += 12;
         return BAMBU_EM_OK;
     }
-    if (s.v2)
-        pack_giant_kernel<1024, true><<<count, 1024, 0, st>>>(v.A, v.W, s.gdesc.as<GiantDesc>() + first, count,
-                                                               s.gbuf.as<uint8_t>(), v.nnz_nonzero, &v.ctrl->err);
-    else
-        pack_giant_kernel<1024, false><<<count, 1024, 0, st>>>(v.A, v.W, s.gdesc.as<GiantDesc>() + first, count,
-                                                                s.gbuf.as<uint8_t>(), v.nnz_nonzero, &v.ctrl->err);
+    pack_giant_kernel<1024><<<count, 1024, 0, st>>>(v.A, s.gdesc.as<GiantDesc>() + first, count, s.gbuf.as<uint8_t>(),
+                                                     v.nnz_nonzero, &v.ctrl->err);
     CUDA_TRY(cudaGetLastError());
     s.launches += 1;
     return BAMBU_EM_OK;

@@ -1,20 +1,18 @@
 // giant.cuh -- the streamed tier: gene groups too large for one SM's shared memory
 // (giant loci: thousands of transcripts, 10^5 read classes, millions of entries).
 //
-//   pack_giant_kernel   one CTA per giant group: raw arena slice -> global-memory image
-//                       (live columns only, rows split into their even / odd streams,
-//                       a column-major copy with rows ascending)
-//   em_giant_kernel     cooperative launch, one CTA per SM; all CTAs iterate on ONE group
-//                       at a time with two grid-wide barriers per EM update:
-//                         E-phase  one thread per live column   c_j, ratio_j      (CSC)
-//                         M-phase  one warp per half-row        ordered partial sums (CSR)
-//                         update   every CTA forms theta' = (s_even + s_odd) / rs and the
-//                                  stopping test redundantly -- no flag exchange needed
+//   pack_giant_kernel   one CTA per group: v1 arena slice -> global-memory image (live columns only, rows split into
+//                       their even / odd streams, a column-major copy with rows ascending, the column side in SELL
+//                       order).  The wire form v2 is packed by giant_pack.cuh with the whole GPU.
+//   em_giant_kernel     cooperative launch, one CTA per SM, split into teams of CTAs; a team iterates on one group at
+//                       a time with two team-wide barriers per EM update:
+//                         E-phase  one lane per live column on the SELL copy      c_j, ratio_j
+//                         M-phase  one warp per block of rows: ordered sums of every parity stream, theta', stopping test
+//                         then every CTA of the team refreshes its private copy of theta (shared memory)
 //
 // Arithmetic and summation order are those of em_sell.cuh / src/em.cpp: each row sum is
 // two sequential chains (even / odd dense positions) added at the end, so results and
-// iteration counts are identical to the reference; a half-row's chain is evaluated by
-// one warp (32 products at a time, added in order).
+// iteration counts are identical to the reference.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -79,9 +77,9 @@ __host__ inline void giant_layout(GiantDesc &d, int64_t M, int64_t N, int64_t e)
 }
 
 // ---- pack ------------------------------------------------------------------------------
-template <int T, bool V2>
+template <int T>
 __global__ void __launch_bounds__(T)
-pack_giant_kernel(ArenaDev A, WireDev W, GiantDesc *__restrict__ descs, int n_giant, uint8_t *__restrict__ gbuf,
+pack_giant_kernel(ArenaDev A, GiantDesc *__restrict__ descs, int n_giant, uint8_t *__restrict__ gbuf,
                   int64_t *__restrict__ nnz_nonzero, int *__restrict__ err_flag)
 {
     __shared__ uint32_t s_warp[34];
@@ -109,74 +107,7 @@ pack_giant_kernel(ArenaDev A, WireDev W, GiantDesc *__restrict__ descs, int n_gi
 
     if (tid == 0) s_nz = 0;
     uint32_t NL, nnzL;
-    if (V2) {
-        // wire form v2: the columns are the live ones, the rows are compacted, rs is given (common.cuh: WireDev)
-        const int64_t row0 = W.grp_row_ptr[g], col0 = W.grp_col_ptr[g], ent0 = W.grp_ent_ptr[g];
-        const uint32_t *rend = W.row_end + row0;
-        const uint16_t *cidx16 = reinterpret_cast<const uint16_t *>(W.cidx + W.grp_idx_off[g]);
-        const uint32_t *cidx32 = reinterpret_cast<const uint32_t *>(W.cidx + W.grp_idx_off[g]);
-        const bool wide = wire_idx_width(N) == 4;
-        const double *av = W.aval + ent0;
-        NL = (uint32_t)N;
-        nnzL = (uint32_t)(W.grp_ent_ptr[g + 1] - ent0);
-        for (int j = tid; j < N; j += T) {
-            double y, kk;
-            wire_col(W, col0 + j, y, kk);
-            Yl[j] = y;
-            KY[j] = __dmul_rn(kk, y);
-            cm[j] = (uint8_t)wire_bit(W.multi_bits, col0 + j);
-            colmap[j] = 0;          // parities seen
-        }
-        for (int j = tid; j <= N; j += T) colcnt[j] = 0;
-        __syncthreads();
-        if (tid == 0) {
-            cm[NL] = 0;
-            if (M > 0 && rend[M - 1] != nnzL) atomicOr(err_flag, kErrRowPtr);
-        }
-        for (int i = tid; i < M; i += T) {
-            const uint32_t lo = i ? rend[i - 1] : 0u, hi = rend[i];
-            uint32_t ne = 0, no = 0;
-            if (hi < lo || hi > nnzL) atomicOr(err_flag, kErrRowPtr);
-            else {
-                int prev = -1;
-                for (uint32_t k = lo; k < hi; ++k) {
-                    const uint32_t c = wide ? cidx32[k] : (uint32_t)cidx16[k];
-                    const uint32_t lj = c >> 1;
-                    if (lj >= NL) { atomicOr(err_flag, kErrColRange); continue; }
-                    if ((int)lj <= prev) atomicOr(err_flag, kErrColOrder);
-                    prev = (int)lj;
-                    if (c & 1u) ++no; else ++ne;
-                }
-            }
-            rs[i] = W.rs[row0 + i];
-            hcnt[2 * i] = ne;
-            hcnt[2 * i + 1] = no;
-        }
-        __syncthreads();
-        const uint32_t kept = block_excl_scan<T>(hcnt, 2 * M, s_warp);
-        for (int t = tid; t < 2 * M; t += T) hp[t] = hcnt[t];
-        if (tid == 0) { hp[2 * M] = kept; s_nz = nnzL; }
-        __syncthreads();
-        nnzL = kept;            // == the group's entry count unless an index was out of range (then an error is set)
-        for (int i = tid; i < M; i += T) {
-            const uint32_t lo = i ? rend[i - 1] : 0u, hi = rend[i];
-            if (hi < lo || hi > (uint32_t)(W.grp_ent_ptr[g + 1] - ent0)) continue;
-            uint32_t pe = hcnt[2 * i], po = hcnt[2 * i + 1];
-            for (uint32_t k = lo; k < hi; ++k) {
-                const uint32_t c = wide ? cidx32[k] : (uint32_t)cidx16[k];
-                const uint32_t lj = c >> 1;
-                if (lj >= NL) continue;
-                const uint32_t pos = (c & 1u) ? po++ : pe++;
-                cidx[pos] = lj;
-                cval[pos] = av[k];
-                eq[pos] = (uint8_t)wire_bit(W.eq_bits, ent0 + k);
-                atomicAdd(&colcnt[lj], 1u);
-                atomicOr(&colmap[lj], 1u << (c & 1u));
-            }
-        }
-        __syncthreads();
-        for (int j = tid; j < N; j += T) if (colmap[j] == 3u) atomicOr(err_flag, kErrParity);
-    } else {
+    {
     const int64_t row0 = A.grp_row_ptr[g], col0 = A.grp_col_ptr[g];
     const int64_t *rnp = A.row_nnz_ptr + row0;
     // A: live columns
@@ -343,71 +274,6 @@ __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int n_c
 }
 
 // ---- EM ------------------------------------------------------------------------------------
-// Ordered sums of the two streams of one row (even columns: [loA, hiA), odd columns: [loB, hiB)) by
-// one warp: 32 products of each stream at a time, then 32 steps that add product q of either stream
-// to its accumulator -- two independent add chains, every lane holding the same accumulators.
-// Software pipeline (the SM issues in order, so a load must be issued well before its first use;
-// L2 latency under this load is several hundred cycles, one batch's add chain ~300): batch b+3
-// loads its values and column indices, batch b+2 gathers its ratios, batch b is multiplied and added.
-template <bool HAZARD>
-__device__ __forceinline__ void row_streams(const uint32_t *__restrict__ cidx, const double *__restrict__ cval,
-                                            uint32_t loA, uint32_t hiA, uint32_t loB, uint32_t hiB, int lane, double th,
-                                            const double *ratio, double *stage /* 64 doubles of this warp */,
-                                            double &sA, double &sB)
-{
-    const uint32_t nA = hiA - loA, nB = hiB - loB, nmax = max(nA, nB);
-    double acc = 0.0;     // lane 0: even-column stream, lane 1: odd-column stream
-    // stage 1 of batches 0 and 1, stage 2 of batch 0
-    auto ld_v = [&](uint32_t lo, uint32_t hi, uint32_t base) { const uint32_t k = lo + base + lane; return (k < hi) ? cval[k] : 0.0; };
-    auto ld_c = [&](uint32_t lo, uint32_t hi, uint32_t base) { const uint32_t k = lo + base + lane; return (k < hi) ? cidx[k] : 0xffffffffu; };
-    auto ld_r = [&](uint32_t c) { return (c != 0xffffffffu) ? __ldcg(ratio + c) : 0.0; };
-    // values / column indices are loaded three batches ahead, ratios gathered two batches ahead
-    double vA0 = ld_v(loA, hiA, 0), vB0 = ld_v(loB, hiB, 0);
-    uint32_t cA0 = ld_c(loA, hiA, 0), cB0 = ld_c(loB, hiB, 0);
-    double vA1 = ld_v(loA, hiA, 32), vB1 = ld_v(loB, hiB, 32);
-    uint32_t cA1 = ld_c(loA, hiA, 32), cB1 = ld_c(loB, hiB, 32);
-    double vA2 = ld_v(loA, hiA, 64), vB2 = ld_v(loB, hiB, 64);
-    uint32_t cA2 = ld_c(loA, hiA, 64), cB2 = ld_c(loB, hiB, 64);
-    double rA0 = ld_r(cA0), rB0 = ld_r(cB0);
-    double rA1 = ld_r(cA1), rB1 = ld_r(cB1);
-    for (uint32_t base = 0; base < nmax; base += 32) {
-        const double vA3 = ld_v(loA, hiA, base + 96), vB3 = ld_v(loB, hiB, base + 96);
-        const uint32_t cA3 = ld_c(loA, hiA, base + 96), cB3 = ld_c(loB, hiB, base + 96);
-        const double rA2 = ld_r(cA2), rB2 = ld_r(cB2);
-        // stage 3: products of batch b, then the ordered adds
-        double tA = __dmul_rn(__dmul_rn(vA0, th), rA0), tB = __dmul_rn(__dmul_rn(vB0, th), rB0);
-        if (HAZARD) {
-            if (tA != tA) tA = 0.0;   // replace(nan, 0)  (src/em.cpp:49)
-            if (tB != tB) tB = 0.0;
-        }
-        const int qa = (int)min(32u, nA - min(nA, base)), qb = (int)min(32u, nB - min(nB, base));
-        // the 2 x 32 products go through shared memory; lanes 0 and 1 add their stream's in order
-        // (a shuffle per step would make the SM's shuffle unit the bottleneck)
-        stage[lane] = tA;
-        stage[32 + lane] = tB;
-        __syncwarp();
-        if (lane < 2) {
-            const double *src = stage + 32 * lane;
-            const int n = lane ? qb : qa;
-            if (n == 32) {
-#pragma unroll
-                for (int q = 0; q < 32; q += 2) {
-                    const double2 v = *reinterpret_cast<const double2 *>(src + q);
-                    acc = __dadd_rn(__dadd_rn(acc, v.x), v.y);
-                }
-            } else {
-                for (int q = 0; q < n; ++q) acc = __dadd_rn(acc, src[q]);
-            }
-        }
-        __syncwarp();
-        vA0 = vA1; vB0 = vB1; rA0 = rA1; rB0 = rB1;
-        vA1 = vA2; vB1 = vB2; rA1 = rA2; rB1 = rB2;
-        vA2 = vA3; vB2 = vB3; cA2 = cA3; cB2 = cB3;
-    }
-    sA = __shfl_sync(0xffffffffu, acc, 0);
-    sB = __shfl_sync(0xffffffffu, acc, 1);
-}
-
 // ---- M-phase of a block of `rb` rows by one warp ------------------------------------------------------------------
 // An ordered sum is a chain of dependent FP64 adds (8.4 cycles each): one row per warp keeps 2 of 32 lanes adding.  Here
 // a warp owns rb rows = 2*rb parity streams (segments): for every batch of 32 entries the whole warp forms the products

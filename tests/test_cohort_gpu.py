@@ -96,3 +96,30 @@ def test_config4_slab_from_long_tables():
     want = host_pipeline(tables, ann, inc)
     check(got, want)
     assert abs(np.nansum(got["CPM"][:, 1]) - 1e6) < 1.0     # no incompatible reads: CPM sums to a million
+
+
+def test_cohort_edge_cases():
+    """an empty cohort, a sample without rows, a sample whose genes are all unobserved, an annotation without any
+    transcript of the tables"""
+    from bambu_b200.quantify import bambu_quantDT_cohort_native
+    rng = np.random.default_rng(3)
+    ann = np.arange(1, 40, dtype=np.int64)
+    out = bambu_quantDT_cohort_native([], ann)
+    assert out["counts"].shape == (39, 0)
+    empty = {"GENEID": [], "txid": [], "eqClassId": [], "nobs": [], "equal": [], "rcWidth": [], "txlen": []}
+    dead = {"GENEID": [5, 5, 9], "txid": [3, 4, 8], "eqClassId": [1, 1, 2], "nobs": [0.0, 0.0, 0.0],
+            "equal": [True, False, True], "rcWidth": [10.0, 20.0, 30.0], "txlen": [100.0, 200.0, 300.0]}
+    live = random_long_table(rng, n_genes=8, shared_tx=False)
+    tables = [live, empty, dead]
+    inc = np.array([4.0, 0.0, 2.0])
+    got = bambu_quantDT_cohort_native(tables, ann, inc, {"degradationBias": False})
+    want = host_pipeline([live], ann, inc[:1], {"degradationBias": False})
+    for n in NAMES:
+        assert_same_doubles(got[n][:, 0], want[n][:, 0], n)
+        assert np.isnan(got[n][:, 1]).all()                              # no row at all: every transcript NA
+    # unobserved genes: their transcripts are zeros (CPM 0 / 2 * 1e6 = 0), the others NA
+    seen = np.isin(ann, [3, 4, 8])
+    assert (got["counts"][seen, 2] == 0).all() and (got["CPM"][seen, 2] == 0).all() and np.isnan(got["counts"][~seen, 2]).all()
+    # an annotation that shares no txid with the tables
+    far = bambu_quantDT_cohort_native([live], np.arange(10_000, 10_020, dtype=np.int64), inc[:1], {"degradationBias": False})
+    assert np.isnan(far["counts"]).all()
