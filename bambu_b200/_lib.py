@@ -60,6 +60,11 @@ SYMBOLS = {
     "bambu_quant_last_used_device": (ctypes.c_int, []),
     "bambu_quantDT_hostpack": (ctypes.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _f64, _f64, _p, _p, _p, _p,
                                               ctypes.POINTER(_i64), ctypes.POINTER(_f64)]),
+    "bambu_equirc_last_error": (ctypes.c_char_p, []),
+    "bambu_equirc_create": (ctypes.c_int, [ctypes.POINTER(_p), _i64, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p]),
+    "bambu_equirc_free": (ctypes.c_int, [_p]),
+    "bambu_equirc_size": (ctypes.c_int, [_p, ctypes.POINTER(_i64)]),
+    "bambu_equirc_table": (ctypes.c_int, [_p] + [ctypes.POINTER(_p)] * 8),
     "bambu_quantDT_cohort": (ctypes.c_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _f64, _f64, _i64, _p, _p, _i32,
                                             _p, _p, _p, _p]),
     "bambu_quantDT_dotC": (None, [_p] * 19),

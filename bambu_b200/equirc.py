@@ -152,3 +152,65 @@ def genEquiRCs(distTable, readClasses, annotation):
         tab["nobs"][k], tab["rcWidth"][k], tab["minRC"][k] = top[c]
         tab["txlen"][k] = ann.txlen[t]
     return tab
+
+
+def genEquiRCs_native(distTable, readClasses, annotation):
+    """:func:`genEquiRCs` done by the native host code of ``libbambu_em.so`` (``bambu_equirc_create``, csrc/equirc.cpp):
+    hash joins on integer columns instead of Python dictionaries of tuples.  Same table, same row order, same class
+    numbering (tests/test_equirc_random.py, tests/test_chr9_e2e.py)."""
+    import ctypes
+    from . import _lib
+    L = _lib.lib()
+    ann_txid = np.ascontiguousarray(annotation["txid"], dtype=np.int64)
+    genes = {}
+    code = lambda g: genes.setdefault(g, len(genes))        # noqa: E731
+    ann_gene = np.array([code(g) for g in annotation["GENEID"]], dtype=np.int64)
+    ptr_ = np.concatenate(([0], np.asarray(annotation["eqClassById_end"], dtype=np.int64))).astype(np.int64)
+    val_ = np.ascontiguousarray(annotation["eqClassById_values"], dtype=np.int64)
+    ew = np.asarray(annotation["exon_width"], dtype=np.float64)
+    ee = np.concatenate(([0], np.asarray(annotation["exon_end"], dtype=np.int64)))
+    txlen = np.array([ew[ee[i]:ee[i + 1]].sum() for i in range(len(ann_txid))], dtype=np.float64)
+    names = list(readClasses["names"])
+    rc_row = {n: k for k, n in enumerate(names)}
+    rc_gene = np.array([code(g) for g in readClasses["GENEID"]], dtype=np.int64)
+    rw = np.asarray(readClasses["exon_width"], dtype=np.float64)
+    rr = np.asarray(readClasses["exon_rank"], dtype=np.float64)
+    re = np.concatenate(([0], np.asarray(readClasses["exon_end"], dtype=np.int64)))
+    first = np.zeros(len(names))
+    total = np.zeros(len(names))
+    for k in range(len(names)):
+        w, r = rw[re[k]:re[k + 1]], rr[re[k]:re[k + 1]]
+        first[k] = w[np.nonzero(r == 1)[0][0]]
+        total[k] = w.sum()
+    n_dt = len(distTable["txid"])
+    dt_rc = np.array([rc_row[r] for r in distTable["readClassId"]], dtype=np.int64)
+    dt_tx = np.ascontiguousarray(distTable["txid"], dtype=np.int64)
+    dt_cnt = np.ascontiguousarray(distTable["readCount"], dtype=np.float64)
+    dt_eq = np.ascontiguousarray(np.asarray(distTable["equal"], dtype=bool), dtype=np.uint8)
+    dt_gene = np.array([code(g) for g in distTable["GENEID"]], dtype=np.int64)
+    dt_un = np.array(["unidentified" in str(a) for a in distTable["annotationTxId"]], dtype=np.uint8)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)       # noqa: E731
+    h = ctypes.c_void_p()
+    rc = L.bambu_equirc_create(ctypes.byref(h), len(ann_txid), p(ann_txid), p(ann_gene), p(ptr_), p(val_), p(txlen), len(names),
+                               p(rc_gene), p(first), p(total), n_dt, p(dt_rc), p(dt_tx), p(dt_cnt), p(dt_eq), p(dt_gene), p(dt_un))
+    if rc:
+        raise ValueError(L.bambu_equirc_last_error().decode())
+    try:
+        n = ctypes.c_int64()
+        L.bambu_equirc_size(h, ctypes.byref(n))
+        n = int(n.value)
+        ptrs = [ctypes.c_void_p() for _ in range(8)]
+        L.bambu_equirc_table(h, *[ctypes.byref(x) for x in ptrs])
+
+        def arr(q, dt):
+            if n == 0:
+                return np.zeros(0, dt)
+            return np.frombuffer((ctypes.c_char * (n * np.dtype(dt).itemsize)).from_address(q.value), dtype=dt).copy()
+        gene_names = list(genes)
+        g = arr(ptrs[0], np.int64)
+        tab = {"GENEID": [gene_names[k] for k in g], "txid": arr(ptrs[1], np.int64), "eqClassId": arr(ptrs[2], np.int64),
+               "nobs": arr(ptrs[3], np.float64), "equal": arr(ptrs[4], np.uint8).astype(bool), "rcWidth": arr(ptrs[5], np.float64),
+               "txlen": arr(ptrs[6], np.float64), "minRC": arr(ptrs[7], np.int64)}
+    finally:
+        L.bambu_equirc_free(h)
+    return tab

@@ -263,6 +263,27 @@ void bambu_quantDT_dotC(const int *n_rows, const int *gene_code, const int *txid
                         const int *degradation_bias, const int *maxiter, const double *minvalue, const double *conv,
                         int *txid_out, double *counts, double *full_length, double *unique_counts, int *n_result,
                         double *d_rate, int *rc);
+/* ---- equivalence read classes from the distance table: genEquiRCs (R/bambu-quantify_utilityFunctions.R:46-192), native
+ * host code (csrc/equirc.cpp) -- the producer of the long table bambu_quantDT takes.  All ids are integers: the caller
+ * codes GENEID (any coding, consistent across the three tables) and refers to a read class by its row in the read-class
+ * table.  Annotation: per transcript txid, gene, its minimal equivalent class eqClassById (eqcls_val[eqcls_ptr[i] ..
+ * eqcls_ptr[i+1]), sorted txids) and its length (sum of exon widths).  Read classes (rowData order): gene, width of the
+ * exon with exon_rank 1, total width.  Distance table: read class row, txid, readCount, equal, gene, and a flag for the
+ * rows whose annotationTxId is "<gene>_unidentified" (dropped, :84).  Output rows in the reference's order: gene, txid,
+ * eqClassId (cur_group_id, 1-based), nobs, equal, rcWidth, txlen, minRC.  Borrowed pointers, valid until _free. */
+typedef struct bambu_equirc bambu_equirc;
+const char *bambu_equirc_last_error(void);
+int bambu_equirc_create(bambu_equirc **out, int64_t n_tx, const int64_t *ann_txid, const int64_t *ann_gene,
+                        const int64_t *eqcls_ptr, const int64_t *eqcls_val, const double *ann_txlen, int64_t n_rc,
+                        const int64_t *rc_gene, const double *rc_first_exon_width, const double *rc_total_width,
+                        int64_t n_dt, const int64_t *dt_rc, const int64_t *dt_txid, const double *dt_read_count,
+                        const uint8_t *dt_equal, const int64_t *dt_gene, const uint8_t *dt_unidentified);
+int bambu_equirc_free(bambu_equirc *p);
+int bambu_equirc_size(const bambu_equirc *p, int64_t *n_rows);
+int bambu_equirc_table(const bambu_equirc *p, const int64_t **gene, const int64_t **txid, const int64_t **eqClassId,
+                       const double **nobs, const uint8_t **equal, const double **rcWidth, const double **txlen,
+                       const int64_t **minRC);
+
 /* ---- the quantification stage of a whole cohort: bplapply(readClassList, bambu.quantify) + combineCountSes ------
  * (R/bambu.R:187-192, R/bambu-quantify.R:22-38, R/bambu_utilityFunctions.R:215-241) for the part after genEquiRCs.
  * Per sample s: the long table (n_rows[s] rows; column pointers [s], as bambu_quantDT takes them; equal / rcWidth /

@@ -12,7 +12,7 @@ from conftest import ROOT
 def _declared_functions():
     src = open(os.path.join(ROOT, "include", "bambu_em.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(bambu_em\w*|bambu_emWithL1|bambu_quant\w*|bambu_wire\w*)\s*\(", src)) - {"bambu_em_plan"})
+    return sorted(set(re.findall(r"\b(bambu_em\w*|bambu_emWithL1|bambu_quant\w*|bambu_wire\w*|bambu_equirc\w*)\s*\(", src)) - {"bambu_em_plan", "bambu_equirc"})
 
 
 @pytest.fixture(scope="module")

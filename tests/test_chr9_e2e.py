@@ -70,3 +70,13 @@ def test_quant_ref_agrees_on_chr9(fx, oracle_mod):
 def test_chr9_through_cuda(fx):
     assays, det = _run(fx, None)      # default EM: libbambu_em.so
     _check(fx, assays, det)
+
+
+def test_native_genEquiRCs_on_chr9(fx):
+    """csrc/equirc.cpp on the bundled run: the 491-row table of the Python mirror, row for row"""
+    from bambu_b200.equirc import genEquiRCs, genEquiRCs_native
+    a = genEquiRCs(fx["distTable"], fx["readClasses"], fx["annotation"])
+    b = genEquiRCs_native(fx["distTable"], fx["readClasses"], fx["annotation"])
+    assert len(b["txid"]) == 491 and len(set(b["eqClassId"])) == 222
+    for col in ("GENEID", "txid", "eqClassId", "nobs", "equal", "rcWidth", "txlen", "minRC"):
+        assert list(a[col]) == list(b[col]), col

@@ -93,6 +93,11 @@ def test_product_genEquiRCs_equals_the_restatement(seed):
     assert len(got["txid"]) == len(want["txid"])
     for col in ("GENEID", "txid", "eqClassId", "nobs", "equal", "rcWidth", "txlen"):
         assert list(got[col]) == list(want[col]), col          # same rows in the same order, same class numbering
+    # the native host code (csrc/equirc.cpp, bambu_equirc_create): same rows, same order, same numbering
+    from bambu_b200.equirc import genEquiRCs_native
+    nat = genEquiRCs_native(fx["distTable"], fx["readClasses"], fx["annotation"])
+    for col in ("GENEID", "txid", "eqClassId", "nobs", "equal", "rcWidth", "txlen", "minRC"):
+        assert list(nat[col]) == list(got[col]), col
     # the annotation side cached for a cohort gives the same table
     cached = AnnotationClasses(fx["annotation"])
     again = genEquiRCs(fx["distTable"], fx["readClasses"], cached)
