@@ -217,3 +217,34 @@ def test_malformed_wire_is_rejected():
     # and the library is still usable afterwards
     est, iters, status = em.abundance_quantification_wire(w)
     assert np.isfinite(est).any()
+
+
+@pytest.mark.gpu
+def test_wire_spill_to_streamed_tier_and_pool_growth(oracle_mod, monkeypatch):
+    """the rarely taken host paths with the wire form: a group the host admits to the resident tier whose padded image
+    does not fit shared memory (flagged by sell_kernel, re-packed by giant_pack.cuh, iterated by the streamed tier), and
+    an image pool that is too small (grown, chunk rerun)"""
+    from bambu_b200.arena import Arena
+    rng = np.random.default_rng(55)
+
+    def locus(M, n_wide, n_unique):
+        N = n_wide + n_unique
+        rows = np.concatenate([np.repeat(np.arange(M), n_wide), rng.integers(0, M, n_unique)])
+        cols = np.concatenate([np.tile(np.arange(n_wide), M), n_wide + np.arange(n_unique)])
+        keep = rng.random(len(rows)) < 0.97
+        keep[M * n_wide:] = True
+        key = np.unique(rows[keep].astype(np.int64) * N + cols[keep])
+        r, c = key // N, key % N
+        aval = rng.uniform(0.05, 1.0, len(key))
+        nobs = 1.0 + rng.negative_binomial(0.5, 0.5 / 40.5, N)
+        K = nobs.sum()
+        rnp = np.concatenate(([0], np.cumsum(np.bincount(r, minlength=M)))).astype(np.int64)
+        return Arena(np.array([0, M], np.int64), np.array([0, N], np.int64), rnp, c.astype(np.int32), aval,
+                     (rng.random(len(key)) < 0.2).astype(np.uint8), nobs / K, np.full(N, K),
+                     (np.bincount(c, minlength=N) > 1).astype(np.uint8), np.arange(M, dtype=np.int32))
+    a = Arena.concatenate([locus(2000, 2, 2100), random_arena(rng, n_groups=6), locus(1500, 3, 1800)])
+    check_wire_against_oracle(oracle_mod, a, maxiter=120)
+    from bambu_b200 import synthetic
+    b = synthetic.config2(scale=0.03)
+    monkeypatch.setenv("BAMBU_EM_POOL_BYTES", "65536")
+    check_wire_against_oracle(oracle_mod, b)
