@@ -63,17 +63,21 @@ class SharedHostTable:
 
     LINE = 64
 
-    def __init__(self, rows_local: int, group=None, pin: bool = True):
+    def __init__(self, rows_local: int = 0, group=None, pin: bool = True, local_shape=None):
+        """``rows_local``: this rank's slice is ``est[3, rows_local]``; or ``local_shape``: any float64 block (e.g. the
+        ``[4, samples, n_tx]`` assays of this rank's share of a cohort)."""
         import mmap
         import os
         import torch
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        shape = tuple(int(x) for x in local_shape) if local_shape is not None else (3, int(rows_local))
         allr = [None] * self.world
-        dist.all_gather_object(allr, int(rows_local), group=group)
-        self.rows = [int(x) for x in allr]
-        sizes = [3 * 8 * r for r in self.rows]
+        dist.all_gather_object(allr, shape, group=group)
+        self.shapes = [tuple(x) for x in allr]
+        self.rows = [x[-1] for x in self.shapes]
+        sizes = [8 * int(np.prod(x)) for x in self.shapes]
         self.header = self.LINE * (self.world + 1)
         off = self.header + np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
         self.buf_bytes = int(sum(sizes))
@@ -102,7 +106,7 @@ class SharedHostTable:
         buf = np.frombuffer(self._map, dtype=np.uint8, count=self.total)
         self._buf = buf
         self._ctr = buf[:self.header].view(np.int64)             # counter of rank r at index r * LINE / 8
-        self._views = [[buf[off[r] + b * self.buf_bytes: off[r + 1] + b * self.buf_bytes].view(np.float64).reshape(3, self.rows[r])
+        self._views = [[buf[off[r] + b * self.buf_bytes: off[r + 1] + b * self.buf_bytes].view(np.float64).reshape(self.shapes[r])
                         for r in range(self.world)] for b in (0, 1)]
         self.step = 0                                            # steps this rank has published
         self._pinned = []
@@ -260,3 +264,43 @@ class EstimateGatherer:
         if self.device.type == "cuda":
             self.torch.cuda.current_stream(self.device).synchronize()
         return self.host
+
+
+def cohort_assays(tables, sample_ids, n_samples_total, annotation_txid, incompatible_totals=None, emParameters=None,
+                  sig_digit=5, quantify=None, group=None):
+    """The quantification stage of a cohort on all ranks of one box: every rank quantifies ITS samples
+    (``tables[k]`` is sample ``sample_ids[k]`` of the cohort; ``shard_samples`` makes such a split) with one
+    ``bambu_quantDT_cohort`` call that writes the four assays of its samples straight into its page-locked slice of a
+    shared host block; rank 0 then assembles the ``n_tx x n_samples_total`` matrices in cohort order -- ``bambu()``'s
+    ``bplapply(readClassList, bambu.quantify)`` + ``combineCountSes`` (R/bambu.R:187-192).  Returns the dict of four
+    matrices on rank 0, ``None`` elsewhere.  ``quantify(tables, annotation_txid, inc, emParameters, sig_digit, out)``
+    defaults to ``quantify.bambu_quantDT_cohort_native`` (tests pass a stand-in)."""
+    import torch.distributed as dist
+    ann = np.ascontiguousarray(annotation_txid, dtype=np.int64)
+    S, T = len(tables), len(ann)
+    if len(sample_ids) != S:
+        raise ValueError("one sample id per table")
+    block = SharedHostTable(group=group, local_shape=(4, max(S, 1), max(T, 1)))
+    out = block.mine
+    inc = np.zeros(S) if incompatible_totals is None else np.asarray(incompatible_totals, dtype=np.float64)
+    if quantify is None:
+        from .quantify import bambu_quantDT_cohort_native
+
+        def quantify(tables, ann, inc, par, sig, out):
+            bambu_quantDT_cohort_native(tables, ann, inc, par, sig, out=out)
+    if S:
+        quantify(tables, ann, inc, emParameters, sig_digit, out)
+    ids = [None] * dist.get_world_size(group)
+    dist.all_gather_object(ids, [int(x) for x in sample_ids], group=group)
+    views = block.gather()
+    res = None
+    if views is not None:
+        names = ("counts", "CPM", "fullLengthCounts", "uniqueCounts")
+        res = {n: np.full((T, int(n_samples_total)), np.nan, order="F") for n in names}
+        for v, sid in zip(views, ids):
+            for k, n in enumerate(names):
+                if len(sid):
+                    res[n][:, sid] = v[k, :len(sid), :T].T
+    dist.barrier(group=group)         # rank 0 has copied: the block may go
+    block.close()
+    return res

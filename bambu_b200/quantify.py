@@ -377,7 +377,7 @@ def bambu_quantDT_native(readClassDt, emParameters=None, host_pack=False):
 
 
 def bambu_quantDT_cohort_native(tables, annotation_txid, incompatible_totals=None, emParameters=None, sig_digit=5,
-                                device_assays=None):
+                                device_assays=None, out=None):
     """The quantification stage of a cohort in ONE library call (``bambu_quantDT_cohort``): what ``bambu()`` does with
     ``bplapply(readClassList, bambu.quantify)`` + ``combineCountSes`` (R/bambu.R:187-192) after ``genEquiRCs`` --
     per sample ``bambu.quantDT``, ``calculateCPM``, ``counts[match(annotation txid, txid)]``, ``round(., sig.digit)``.
@@ -385,7 +385,9 @@ def bambu_quantDT_cohort_native(tables, annotation_txid, incompatible_totals=Non
     ``tables``: list of long tables (dicts as :func:`bambu_quantDT` takes them; GENEID already integer-coded or any
     hashable); ``incompatible_totals[s]`` = ``sum(incompatibleCounts$counts)`` of sample s.  Returns a dict of four
     ``n_tx x n_samples`` matrices (Fortran order, like R) plus ``d_rate`` and ``used_device`` per sample.
-    ``device_assays``: optional raw device address of a ``4 * n_samples * n_tx`` float64 block to fill as well."""
+    ``device_assays``: optional raw device address of a ``4 * n_samples * n_tx`` float64 block to fill as well;
+    ``out``: optional C-contiguous float64 HOST array ``[4, n_samples, n_tx]`` the library writes into (e.g. a
+    page-locked slice of ``dist.SharedHostTable``)."""
     import ctypes
     from . import _lib
     par = setEmParameters(emParameters)
@@ -421,7 +423,12 @@ def bambu_quantDT_cohort_native(tables, annotation_txid, incompatible_totals=Non
     pa = {k: ptr_array(v) for k, v in cols.items()}
     if S and len({v is None for v in cols["equal"]}) > 1:
         raise ValueError("either every table carries an `equal` column or none does")
-    assays = np.zeros((4, max(S, 1), max(T, 1)), dtype=np.float64)
+    if out is None:
+        assays = np.zeros((4, max(S, 1), max(T, 1)), dtype=np.float64)
+    else:
+        assays = out
+        if assays.dtype != np.float64 or not assays.flags.c_contiguous or assays.shape != (4, max(S, 1), max(T, 1)):
+            raise ValueError("out must be a C-contiguous float64 array of shape [4, n_samples, n_tx]")
     d_rate = np.zeros(max(S, 1), np.float64)
     used = np.zeros(max(S, 1), np.int32)
     inc = np.zeros(max(S, 1), np.float64) if incompatible_totals is None else c(incompatible_totals, np.float64)

@@ -93,3 +93,43 @@ def test_shard_groups_by_weight_places_giants_first():
     assert sorted(int(np.argmax(w[x])) >= 0 for x in sh) and len({tuple(x) for x in sh}) == 3
     heavy = [set(x) & {2, 4, 6} for x in sh]
     assert all(len(h) == 1 for h in heavy)           # one giant locus per rank
+
+
+def _cohort_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_total, n_tx = 7, 11
+    shards = bdist.shard_samples([5, 1, 9, 3, 3, 7, 2], world)
+    mine = [int(s) for s in shards[rank]]
+
+    def fake_quantify(tables, ann, inc, par, sig, out):          # stands in for bambu_quantDT_cohort (needs a GPU)
+        for k, t in enumerate(tables):
+            for a in range(4):
+                out[a, k, :len(ann)] = 1000 * a + 10 * t["sample"] + np.arange(len(ann)) / 100 + inc[k]
+    tables = [{"sample": s} for s in mine]
+    res = bdist.cohort_assays(tables, mine, n_total, np.arange(1, n_tx + 1), [0.5] * len(mine), quantify=fake_quantify)
+    if rank == 0:
+        ok = set(res) == {"counts", "CPM", "fullLengthCounts", "uniqueCounts"}
+        for a, name in enumerate(("counts", "CPM", "fullLengthCounts", "uniqueCounts")):
+            want = np.array([[1000 * a + 10 * s + i / 100 + 0.5 for s in range(n_total)] for i in range(n_tx)])
+            ok &= res[name].shape == (n_tx, n_total) and np.array_equal(res[name], want)
+        q.put(bool(ok))
+    else:
+        q.put(res is None)
+    dist.destroy_process_group()
+
+
+def test_cohort_assays_assembled_on_rank0_world2():
+    """samples sharded over two ranks, every rank writes its assays into the shared block, rank 0 assembles the
+    n_tx x n_samples matrices in cohort order (combineCountSes)"""
+    world = 2
+    ctx = tmp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cohort_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(res)
