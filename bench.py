@@ -13,9 +13,15 @@ data-path collective (weak scaling: every rank owns ``S`` samples).
 
 metric   EM nnz-iterations / s  =  sum_groups nnz_g * iters_g / time, nnz_g counting
          the entries with aval != 0, iters_g the EM updates of the group
-value    device time (CUDA events on the launch stream), arena resident in HBM
-e2e      host wall clock around the C-ABI call ``bambu_em_batched`` with pinned HOST
-         buffers: plan + H2D + kernels + D2H inside, plus the NCCL gather to rank 0 at N > 1
+value    device time (CUDA events on the launch stream), wire form of the arena resident in HBM
+e2e      host wall clock around the C-ABI call ``bambu_em_batched_v2`` with pinned HOST
+         buffers: plan + H2D + kernels + D2H inside; at N > 1 every rank's tables are on rank 0's
+         host (one shared, page-locked table) when the step ends
+also     parity (cohort sample 0 of the e2e run vs the sparse oracle; the run fails if it differs),
+         roofline.binding / traffic (from profiles/r2_roofline.json, an ncu capture), cpu_baseline,
+         strong (the 100-sample cohort over N GPUs via dist.shard_samples), config3 / config3_sharded
+         (giant loci, groups over N GPUs via dist.shard_groups_by_weight), config2_single,
+         quantDT_stage, quant_stage_cohort (bambu_quantDT_cohort vs the stage on all host cores)
 """
 from __future__ import annotations
 
