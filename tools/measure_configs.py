@@ -47,7 +47,7 @@ def measure(name, a, cpu=True, reps=3):
 def main():
     t0 = time.time()
     measure("config2 single sample", S.config2())
-    a3 = S.config3_arena(c3_scale, workers=min(16, os.cpu_count() or 8))       # locus by locus (seconds instead of minutes)
+    a3 = S.config3_arena(c3_scale, workers=min(16, os.cpu_count() or 8), mp_context="forkserver")   # locus by locus
     measure(f"config3 skewed loci (scale {c3_scale:g}: {S.config3_plan(c3_scale).n_giant} giant)", a3)
     ann4 = S.annotation_for("config4")
     measure(f"config4 cohort slab ({n_cohort} samples)", Arena.concatenate([S.cohort_sample(ann4, s) for s in range(n_cohort)]), cpu=False)
