@@ -81,7 +81,8 @@ def test_r_shim_typechecks(built_lib):
     shim = os.path.join(ROOT, "r", "b200_shim.c")
     src = re.sub(r"/\*.*?\*/", "", open(shim).read(), flags=re.S)
     used = set(re.findall(r"\b(bambu_(?:em|emWithL1|quant|wire)\w*)\s*\(", src))
-    assert {"bambu_em_batched", "bambu_emWithL1", "bambu_quantDT_dotC", "bambu_em_last_error", "bambu_em_shutdown"} <= used
+    assert {"bambu_em_batched", "bambu_em_batched_v2", "bambu_wire_create", "bambu_emWithL1", "bambu_quantDT_dotC",
+            "bambu_em_last_error", "bambu_em_shutdown"} <= used
     L = built_lib.lib()
     for n in used:
         assert n in built_lib.SYMBOLS and hasattr(L, n), n
