@@ -280,6 +280,17 @@ def test_streamed_tier_forced_on_random_groups(em, oracle_mod, monkeypatch, seed
         check_against_oracle(em, oracle_mod, a, **par)
 
 
+def test_streamed_tier_single_row_blocks(em, oracle_mod, monkeypatch):
+    """the M-phase of the streamed tier works on blocks of 2 rows per warp; loci with more than ~24 000 transcripts
+    leave shared memory for 1-row blocks only -- the same code path, forced here"""
+    monkeypatch.setenv("BAMBU_EM_FORCE_GIANT", "1")
+    monkeypatch.setenv("BAMBU_EM_GIANT_RB", "1")
+    rng = np.random.default_rng(2100)
+    a = random_arena(rng, n_groups=25, max_m=70, max_n=150)
+    check_against_oracle(em, oracle_mod, a)
+    check_against_oracle(em, oracle_mod, a, conv=1e-5)
+
+
 def giant_locus_arena(rng, M, N, k_mean, observed=0.4):
     from bambu_b200.arena import Arena
     k = 1 + rng.binomial(M - 1, k_mean / M, N)
